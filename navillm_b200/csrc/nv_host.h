@@ -1,0 +1,46 @@
+// navillm_b200 — host-side helpers shared by the C-ABI translation units (internal).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define NV_OK 0
+#define NV_ERR_BAD_ARG (-1)
+#define NV_ERR_NO_DEVICE (-2)
+#define NV_ERR_UNSUPPORTED (-3)
+
+extern "C" const char* nv_last_error(void);
+
+namespace nv {
+
+void set_error(const char* fmt, ...);
+
+// Returns the positive cudaError_t after recording its string.
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define NV_CUDA(call)                                                          \
+  do {                                                                         \
+    cudaError_t _e = (call);                                                   \
+    if (_e != cudaSuccess) return ::nv::cuda_fail(_e, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define NV_REQUIRE(cond, ...)        \
+  do {                               \
+    if (!(cond)) {                   \
+      ::nv::set_error(__VA_ARGS__);  \
+      return NV_ERR_BAD_ARG;         \
+    }                                \
+  } while (0)
+
+#define NV_LAUNCH_CHECK() NV_CUDA(cudaGetLastError())
+
+int sm_count();
+
+// 2-D bf16/fp32 tiled tensor map with 128-byte swizzle. `inner` is the contiguous dimension.
+// Out-of-bounds box elements read as zero (and are clipped on store).
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
+
+}  // namespace nv

@@ -1,0 +1,70 @@
+"""tcgen05 bf16 GEMM (csrc/gemm_bf16.cu) against a plain PyTorch fp32 reference of the same op.
+
+Tolerance: inputs are bf16, accumulation fp32, output rounded once to bf16 -> the only admissible
+difference from an fp32 reference rounded to bf16 is accumulation order: |diff| <= 2 bf16 ulp of the
+result magnitude (rtol 1.6e-2 covers 2 ulp at 8 mantissa bits) plus a small atol for cancellation.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(a, b, a_mn, b_mn):
+    A = a.float().t() if a_mn else a.float()
+    B = b.float() if b_mn else b.float().t()
+    return A @ B
+
+
+SHAPES = [
+    (128, 128, 64), (128, 256, 128), (256, 512, 4096), (384, 4096, 4096), (1000, 1032, 520),
+    (77, 200, 72), (4096, 12288, 4096), (2048, 4096, 11008),
+]
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_matches_fp32_reference(cuda_dev, M, N, K, a_mn, b_mn):
+    from navillm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    a = torch.randn((K, M) if a_mn else (M, K), generator=g).to(cuda_dev, torch.bfloat16)
+    b = torch.randn((K, N) if b_mn else (N, K), generator=g).to(cuda_dev, torch.bfloat16)
+    for bn in (128, 256):
+        out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, block_n=bn)
+        torch.cuda.synchronize()
+        ref = _ref(a, b, a_mn, b_mn)
+        err = (out.float() - ref).abs()
+        tol = 1.6e-2 * ref.abs() + 2e-2 * (K ** 0.5) * 0.05
+        assert bool((err <= tol).all()), f"bn={bn} max err {err.max().item()} (ref max {ref.abs().max().item()})"
+
+
+def test_gemm_residual_add_and_strided(cuda_dev):
+    from navillm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 300, 4096, 512
+    big = torch.randn(M, 3 * K, generator=g).to(cuda_dev, torch.bfloat16)
+    a = big[:, K:2 * K]                      # strided view: lda = 3K
+    w = torch.randn(N, K, generator=g).to(cuda_dev, torch.bfloat16)
+    res = torch.randn(M, N, generator=g).to(cuda_dev, torch.bfloat16)
+    out = ops.gemm(a, w, addend=res)
+    torch.cuda.synchronize()
+    ref = ((a.float() @ w.float().t()).to(torch.bfloat16).float() + res.float()).to(torch.bfloat16)
+    err = (out.float() - ref.float()).abs()
+    assert bool((err <= 1.6e-2 * ref.float().abs() + 0.25).all()), err.max().item()
+    # in-place accumulation (gradient accumulation form): C = bf16(acc) + C
+    acc = res.clone()
+    ops.gemm(a, w, out=acc, addend=acc)
+    torch.cuda.synchronize()
+    assert torch.equal(acc, out)
+
+
+def test_gemm_fp32_out(cuda_dev):
+    from navillm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(9)
+    M, N, K = 130, 1000, 256
+    a = torch.randn(M, K, generator=g).to(cuda_dev, torch.bfloat16)
+    w = torch.randn(N, K, generator=g).to(cuda_dev, torch.bfloat16)
+    out = ops.gemm(a, w, out_f32=True)
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t()
+    assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), (out - ref).abs().max().item()
