@@ -26,6 +26,11 @@ SHAPES = [
 @pytest.mark.parametrize("M,N,K", SHAPES)
 def test_gemm_matches_fp32_reference(cuda_dev, M, N, K, a_mn, b_mn):
     from navillm_b200 import ops
+    # an MN-major operand is stored [K, MN]: its leading dimension (MN) must be a multiple of 8 elements
+    if a_mn:
+        M = (M + 7) // 8 * 8
+    if b_mn:
+        N = (N + 7) // 8 * 8
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
     a = torch.randn((K, M) if a_mn else (M, K), generator=g).to(cuda_dev, torch.bfloat16)
     b = torch.randn((K, N) if b_mn else (N, K), generator=g).to(cuda_dev, torch.bfloat16)
