@@ -48,3 +48,181 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                            i64(out.stride(0)), ptr(addend), i64(addend.stride(0) if addend is not None else 0),
                            i32(M), i32(N), i32(K), u32(flags), i32(block_n), stream_ptr()), "nv_gemm_bf16")
     return out
+
+
+def _qblocks(seqlens) -> int:
+    return int(sum((int(l) + 127) // 128 for l in seqlens))
+
+
+def attn_fwd(qkv: torch.Tensor, cu_seqlens: torch.Tensor, seqlens, n_heads: int, *, out: torch.Tensor | None = None,
+             lse: torch.Tensor | None = None, scale: float | None = None):
+    """Causal self-attention over packed sequences (csrc/attn_fwd.cu).
+
+    qkv: [T, 3*H*128] bf16 (q | k | v column blocks, RoPE already applied); cu_seqlens: int32 [B+1] on the
+    device; seqlens: host list of the B lengths.  Returns (o [T, H*128] bf16, lse [H, T] fp32).
+    """
+    _rowmajor(qkv, "qkv")
+    T, W = qkv.shape
+    hd = 128
+    assert W == 3 * n_heads * hd and qkv.dtype == bf16
+    B = len(seqlens)
+    assert cu_seqlens.dtype == torch.int32 and cu_seqlens.numel() == B + 1 and cu_seqlens.is_cuda
+    if out is None:
+        out = torch.empty((T, n_heads * hd), dtype=bf16, device=qkv.device)
+    if lse is None:
+        lse = torch.empty((n_heads, T), dtype=torch.float32, device=qkv.device)
+    if scale is None:
+        scale = hd ** -0.5
+    q, k, v = qkv[:, : n_heads * hd], qkv[:, n_heads * hd: 2 * n_heads * hd], qkv[:, 2 * n_heads * hd:]
+    lib = _lib.load()
+    check(lib.nv_attn_fwd(ptr(q), i64(qkv.stride(0)), ptr(k), i64(qkv.stride(0)), ptr(v), i64(qkv.stride(0)), ptr(out),
+                          i64(out.stride(0)), ptr(lse), ptr(cu_seqlens), i32(B), i32(T), i32(n_heads), i32(hd),
+                          i32(_qblocks(seqlens)), f32(scale), stream_ptr()), "nv_attn_fwd")
+    return out, lse
+
+
+# ---------------------------------------------------------------------------------------------------
+# row-wise LM kernels (csrc/lm_ops.cu)
+# ---------------------------------------------------------------------------------------------------
+def rmsnorm_fwd(x, w, eps, *, out=None, rstd=None):
+    _rowmajor(x, "x")
+    T, D = x.shape
+    if out is None:
+        out = torch.empty((T, D), dtype=bf16, device=x.device)
+    if rstd is None:
+        rstd = torch.empty((T,), dtype=torch.float32, device=x.device)
+    check(_lib.load().nv_rmsnorm_fwd(ptr(x), i64(x.stride(0)), ptr(w), ptr(out), i64(out.stride(0)), ptr(rstd), i32(T),
+                                     i32(D), f32(eps), stream_ptr()), "nv_rmsnorm_fwd")
+    return out, rstd
+
+
+_ws_cache: dict = {}
+
+
+def _workspace(dev, nfloat: int) -> torch.Tensor:
+    key = (dev.index, "f32")
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nfloat:
+        ws = torch.empty((max(nfloat, 1 << 20),), dtype=torch.float32, device=dev)
+        _ws_cache[key] = ws
+    return ws
+
+
+def rmsnorm_bwd(x, w, rstd, dy, *, dres=None, dx=None, dw=None, accumulate_dw=True):
+    """dx = rmsnorm'(dy) (+ dres); dw (bf16 [D]) is accumulated in place when given."""
+    _rowmajor(x, "x"); _rowmajor(dy, "dy")
+    T, D = x.shape
+    lib = _lib.load()
+    if dx is None:
+        dx = torch.empty((T, D), dtype=bf16, device=x.device)
+    ws = _workspace(x.device, lib.nv_rmsnorm_bwd_partials() * D)
+    check(lib.nv_rmsnorm_bwd(ptr(x), i64(x.stride(0)), ptr(w), ptr(rstd), ptr(dy), i64(dy.stride(0)), ptr(dres),
+                             i64(dres.stride(0) if dres is not None else 0), ptr(dx), i64(dx.stride(0)), ptr(dw),
+                             i32(1 if accumulate_dw else 0), ptr(ws), i32(T), i32(D), stream_ptr()), "nv_rmsnorm_bwd")
+    return dx
+
+
+def rope_(x, pos, cos_t, sin_t, n_heads, head_dim=128, backward=False):
+    """In-place rotate-half RoPE on the first n_heads*head_dim columns of x ([T, ld] bf16)."""
+    _rowmajor(x, "x")
+    assert pos.dtype == torch.int32
+    check(_lib.load().nv_rope_inplace(ptr(x), i64(x.stride(0)), ptr(pos), ptr(cos_t), ptr(sin_t), i32(x.shape[0]),
+                                      i32(n_heads), i32(head_dim), i32(1 if backward else 0), stream_ptr()),
+          "nv_rope_inplace")
+    return x
+
+
+def swiglu_fwd(gu, *, out=None):
+    _rowmajor(gu, "gu")
+    T, F2 = gu.shape
+    F = F2 // 2
+    if out is None:
+        out = torch.empty((T, F), dtype=bf16, device=gu.device)
+    check(_lib.load().nv_swiglu_fwd(ptr(gu), i64(gu.stride(0)), ptr(out), i64(out.stride(0)), i32(T), i32(F),
+                                    stream_ptr()), "nv_swiglu_fwd")
+    return out
+
+
+def swiglu_bwd(gu, dh, *, out=None):
+    T, F2 = gu.shape
+    if out is None:
+        out = torch.empty((T, F2), dtype=bf16, device=gu.device)
+    check(_lib.load().nv_swiglu_bwd(ptr(gu), i64(gu.stride(0)), ptr(dh), i64(dh.stride(0)), ptr(out),
+                                    i64(out.stride(0)), i32(T), i32(F2 // 2), stream_ptr()), "nv_swiglu_bwd")
+    return out
+
+
+def embed_fwd(ids, E, vis_src=None, vis=None, *, out=None):
+    T = ids.numel()
+    V, D = E.shape
+    assert ids.dtype == torch.int32
+    if out is None:
+        out = torch.empty((T, D), dtype=bf16, device=E.device)
+    if vis is not None:
+        assert vis.dtype == torch.float32 and vis.is_contiguous() and vis_src.dtype == torch.int32
+    check(_lib.load().nv_embed_fwd(ptr(ids), ptr(E), i32(V), ptr(vis_src if vis is not None else None), ptr(vis),
+                                   ptr(out), i32(T), i32(D), stream_ptr()), "nv_embed_fwd")
+    return out
+
+
+def embed_bwd_vis(dx, vis_src, n_vis):
+    T, D = dx.shape
+    dvis = torch.zeros((n_vis, D), dtype=torch.float32, device=dx.device)
+    check(_lib.load().nv_embed_bwd_vis(ptr(dx), ptr(vis_src), ptr(dvis), i32(T), i32(D), stream_ptr()),
+          "nv_embed_bwd_vis")
+    return dvis
+
+
+def embed_bwd_weight_(dx, ids, dE):
+    """dE[ids[t]] += dx[t] (deterministic: tokens are sorted by id, one owner per distinct id)."""
+    T, D = dx.shape
+    sorted_ids, order = torch.sort(ids.to(torch.int64), stable=True)
+    check(_lib.load().nv_embed_bwd_weight(ptr(dx), ptr(order.to(torch.int32)), ptr(sorted_ids.to(torch.int32)), ptr(dE),
+                                          i32(T), i32(D), stream_ptr()), "nv_embed_bwd_weight")
+    return dE
+
+
+def gather_rows(src, rows, *, out=None):
+    R, D = rows.numel(), src.shape[1]
+    if out is None:
+        out = torch.empty((R, D), dtype=bf16, device=src.device)
+    check(_lib.load().nv_gather_rows(ptr(src), i64(src.stride(0)), ptr(rows), ptr(out), i64(out.stride(0)), i32(R),
+                                     i32(D), stream_ptr()), "nv_gather_rows")
+    return out
+
+
+def scatter_rows_(src, rows, dst):
+    R, D = rows.numel(), src.shape[1]
+    check(_lib.load().nv_scatter_rows(ptr(src), i64(src.stride(0)), ptr(rows), ptr(dst), i64(dst.stride(0)), i32(R),
+                                      i32(D), stream_ptr()), "nv_scatter_rows")
+    return dst
+
+
+def head_fwd(x, W, bias):
+    R, D = x.shape
+    O = W.shape[0]
+    out = torch.empty((R, O), dtype=bf16, device=x.device)
+    check(_lib.load().nv_head_fwd(ptr(x), i64(x.stride(0)), ptr(W), ptr(bias), ptr(out), i32(R), i32(O), i32(D),
+                                  stream_ptr()), "nv_head_fwd")
+    return out
+
+
+def head_bwd(dy, x, W, *, dW=None, db=None, need_dx=True):
+    R, D = x.shape
+    O = W.shape[0]
+    dx = torch.empty((R, D), dtype=bf16, device=x.device) if need_dx else None
+    check(_lib.load().nv_head_bwd(ptr(dy), ptr(x), i64(x.stride(0)), ptr(W), ptr(dx), i64(dx.stride(0) if need_dx else 0),
+                                  ptr(dW), ptr(db), i32(R), i32(O), i32(D), stream_ptr()), "nv_head_bwd")
+    return dx
+
+
+def ce_fwd_bwd(logits, labels, special_ids, *, grad_scale=None):
+    """Per-row masked CE on bf16 logits; returns (row_loss fp32 [N], dlogits bf16 [N,V] or None)."""
+    N, V = logits.shape
+    row_loss = torch.empty((N,), dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty((N, V), dtype=bf16, device=logits.device) if grad_scale is not None else None
+    check(_lib.load().nv_ce_fwd_bwd(ptr(logits), i64(logits.stride(0)), ptr(labels), ptr(special_ids),
+                                    i32(special_ids.numel()), ptr(row_loss), ptr(dlogits),
+                                    i64(dlogits.stride(0) if dlogits is not None else 0), i32(N), i32(V),
+                                    f32(grad_scale if grad_scale is not None else 0.0), stream_ptr()), "nv_ce_fwd_bwd")
+    return row_loss, dlogits

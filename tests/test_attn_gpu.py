@@ -1,0 +1,46 @@
+"""tcgen05 flash attention (csrc/attn_fwd.cu, attn_bwd.cu) against a plain PyTorch fp32 reference.
+
+Tolerance (forward): q,k,v are bf16; the kernel keeps S and the running softmax in fp32 and rounds P to
+bf16 before the PV product and O to bf16 at the end, like the reference's eager path (fp32 softmax cast
+to bf16, bf16 matmul).  |o - o_ref| <= 2e-2 * max|o_ref| covers the bf16 rounding of P (2^-9 relative
+per probability) and of O.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HD = 128
+
+
+def ref_attention(qkv, seqlens, H):
+    T = qkv.shape[0]
+    q, k, v = [x.float().view(T, H, HD) for x in qkv.split(H * HD, dim=1)]
+    o = torch.zeros(T, H, HD, device=qkv.device)
+    lse = torch.zeros(H, T, device=qkv.device)
+    s0 = 0
+    for L in seqlens:
+        qs, ks, vs = q[s0:s0 + L].transpose(0, 1), k[s0:s0 + L].transpose(0, 1), v[s0:s0 + L].transpose(0, 1)
+        sc = qs @ ks.transpose(1, 2) * HD ** -0.5
+        mask = torch.ones(L, L, device=qkv.device, dtype=torch.bool).tril()
+        sc = sc.masked_fill(~mask, float("-inf"))
+        lse[:, s0:s0 + L] = torch.logsumexp(sc, dim=-1)
+        o[s0:s0 + L] = (torch.softmax(sc, dim=-1) @ vs).transpose(0, 1)
+        s0 += L
+    return o.reshape(T, H * HD), lse
+
+
+@pytest.mark.parametrize("seqlens,H", [([128], 1), ([256], 2), ([100], 2), ([1, 129, 300], 2), ([1024, 517, 640], 4),
+                                       ([2048], 2)])
+def test_attn_fwd(cuda_dev, seqlens, H):
+    from navillm_b200 import ops
+    T = sum(seqlens)
+    g = torch.Generator(device="cpu").manual_seed(T + H)
+    qkv = (torch.randn(T, 3 * H * HD, generator=g) * 1.5).to(cuda_dev, torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(seqlens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+    o, lse = ops.attn_fwd(qkv, cu, seqlens, H)
+    torch.cuda.synchronize()
+    o_ref, lse_ref = ref_attention(qkv, seqlens, H)
+    err = (o.float() - o_ref).abs().max().item()
+    assert err <= 2e-2 * o_ref.abs().max().item(), f"o err {err}"
+    assert torch.allclose(lse, lse_ref, rtol=1e-3, atol=2e-3), (lse - lse_ref).abs().max().item()
