@@ -177,8 +177,11 @@ def embed_bwd_weight_(dx, ids, dE):
     """dE[ids[t]] += dx[t] (deterministic: tokens are sorted by id, one owner per distinct id)."""
     T, D = dx.shape
     sorted_ids, order = torch.sort(ids.to(torch.int64), stable=True)
-    check(_lib.load().nv_embed_bwd_weight(ptr(dx), ptr(order.to(torch.int32)), ptr(sorted_ids.to(torch.int32)), ptr(dE),
-                                          i32(T), i32(D), stream_ptr()), "nv_embed_bwd_weight")
+    # keep the int32 copies referenced until after the launch: a temporary freed inside the argument
+    # list would hand its block back to the caching allocator before the kernel reads it
+    order32, sorted32 = order.to(torch.int32), sorted_ids.to(torch.int32)
+    check(_lib.load().nv_embed_bwd_weight(ptr(dx), ptr(order32), ptr(sorted32), ptr(dE), i32(T), i32(D), stream_ptr()),
+          "nv_embed_bwd_weight")
     return dE
 
 
@@ -226,3 +229,25 @@ def ce_fwd_bwd(logits, labels, special_ids, *, grad_scale=None):
                                     i64(dlogits.stride(0) if dlogits is not None else 0), i32(N), i32(V),
                                     f32(grad_scale if grad_scale is not None else 0.0), stream_ptr()), "nv_ce_fwd_bwd")
     return row_loss, dlogits
+
+
+def attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Tensor, cu_seqlens: torch.Tensor, seqlens,
+             n_heads: int, *, dqkv: torch.Tensor | None = None, scale: float | None = None) -> torch.Tensor:
+    """Backward of attn_fwd (csrc/attn_bwd.cu): returns dqkv [T, 3*H*128] bf16 (dq | dk | dv)."""
+    T, W = qkv.shape
+    hd = 128
+    HD = n_heads * hd
+    if dqkv is None:
+        dqkv = torch.empty((T, W), dtype=bf16, device=qkv.device)
+    if scale is None:
+        scale = hd ** -0.5
+    dvec = _workspace(qkv.device, n_heads * T + 16)
+    q, k, v = qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:]
+    dq, dk, dv = dqkv[:, :HD], dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:]
+    ld = qkv.stride(0)
+    check(_lib.load().nv_attn_bwd(ptr(q), i64(ld), ptr(k), i64(ld), ptr(v), i64(ld), ptr(o), i64(o.stride(0)), ptr(do),
+                                  i64(do.stride(0)), ptr(lse), ptr(dvec), ptr(dq), i64(dqkv.stride(0)), ptr(dk),
+                                  i64(dqkv.stride(0)), ptr(dv), i64(dqkv.stride(0)), ptr(cu_seqlens), i32(len(seqlens)),
+                                  i32(T), i32(n_heads), i32(hd), i32(_qblocks(seqlens)), f32(scale), stream_ptr()),
+          "nv_attn_bwd")
+    return dqkv

@@ -44,3 +44,25 @@ def test_attn_fwd(cuda_dev, seqlens, H):
     err = (o.float() - o_ref).abs().max().item()
     assert err <= 2e-2 * o_ref.abs().max().item(), f"o err {err}"
     assert torch.allclose(lse, lse_ref, rtol=1e-3, atol=2e-3), (lse - lse_ref).abs().max().item()
+
+
+@pytest.mark.parametrize("seqlens,H", [([128], 1), ([256], 1), ([100], 2), ([1, 129, 300], 2), ([640, 517], 2)])
+def test_attn_bwd(cuda_dev, seqlens, H):
+    """Backward against autograd of the fp32 reference.  The kernel rounds P and dS to bf16 before the
+    dV/dK/dQ products (2^-9 relative per element) and the gradients to bf16: 3e-2 of the gradient's max."""
+    from navillm_b200 import ops
+    T = sum(seqlens)
+    g = torch.Generator(device="cpu").manual_seed(T * 3 + H)
+    qkv = torch.randn(T, 3 * H * HD, generator=g).to(cuda_dev, torch.bfloat16)
+    do = torch.randn(T, H * HD, generator=g).to(cuda_dev, torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(seqlens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+    o, lse = ops.attn_fwd(qkv, cu, seqlens, H)
+    dqkv = ops.attn_bwd(qkv, o, do, lse, cu, seqlens, H)
+    torch.cuda.synchronize()
+    qa = qkv.float().requires_grad_(True)
+    o_ref, _ = ref_attention(qa, seqlens, H)
+    o_ref.backward(do.float())
+    for name, sl in (("dq", slice(0, H * HD)), ("dk", slice(H * HD, 2 * H * HD)), ("dv", slice(2 * H * HD, None))):
+        a, b = dqkv[:, sl].float(), qa.grad[:, sl]
+        err = (a - b).abs().max().item()
+        assert err <= 3e-2 * b.abs().max().item(), f"{name} err {err} vs max {b.abs().max().item()}"
