@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace nv {
 
@@ -63,14 +64,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (error surfaces on the host) instead of hanging the GPU box.
-#ifndef NV_MBAR_SPIN_LIMIT
-#define NV_MBAR_SPIN_LIMIT (1u << 26)
+// Bounded wait: a protocol bug traps after ~2 s (error surfaces on the host as a launch failure)
+// instead of hanging the GPU box.
+#ifndef NV_MBAR_TIMEOUT_CYCLES
+#define NV_MBAR_TIMEOUT_CYCLES (4000000000ll)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > NV_MBAR_SPIN_LIMIT) __trap();
+    if ((++spins & 255u) == 0 && clock64() - t0 > NV_MBAR_TIMEOUT_CYCLES) {
+      printf("navillm_b200: mbarrier timeout block (%d,%d) thread %d bar@%u parity %u\n", (int)blockIdx.x,
+             (int)blockIdx.y, (int)threadIdx.x, smem_u32(bar), parity);
+      __trap();
+    }
   }
 }
 

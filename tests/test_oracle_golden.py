@@ -1,0 +1,139 @@
+"""Pin the CPU oracle (oracle/navillm_oracle.py) against golden vectors produced by the UNMODIFIED
+reference code (tests/golden/make_golden.py, run in the authoring container where /root/reference is
+mounted).  CPU only: runs under `-m "not gpu"`.
+
+Tolerances: the oracle restates the same torch arithmetic in the same dtypes, so fp32 results agree to
+accumulation-order noise (1e-5 relative) and the bf16 LM path to 1 bf16 ulp on logits / hidden states.
+"""
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from oracle import navillm_oracle as O  # noqa: E402
+from navillm_b200.tokenizer import SyntheticTokenizer  # noqa: E402
+
+GOLD = Path(__file__).resolve().parent / "golden"
+
+
+def load(precision):
+    g = torch.load(GOLD / f"nav_{precision}.pt", weights_only=False)
+    d = g["meta"]["dims"]
+    tok = SyntheticTokenizer(base_vocab=d["base_vocab"])
+    cfg = O.OracleConfig(hidden=d["hidden"], n_layers=d["n_layers"], n_heads=d["n_heads"], inter=d["inter"],
+                         vocab=len(tok), image_feat_size=d["image_feat_size"], obj_feat_size=d["obj_feat_size"],
+                         pano_hidden=d["pano_hidden"], pano_heads=d["pano_heads"], pano_inter=d["pano_inter"],
+                         cand_id=tok.special["<cand>"], hist_id=tok.special["<hist>"], obj_id=tok.special["<obj>"],
+                         cls_ids=(tok.special["<cls_1>"], tok.special["<cls_2>"]), precision=precision)
+    return g, cfg, tok
+
+
+def tol(precision):
+    return dict(rtol=2e-5, atol=2e-5) if precision == "fp32" else dict(rtol=1.6e-2, atol=1.6e-2)
+
+
+def nav_batch(g, pano_embeds, pano_masks):
+    B = pano_embeds.shape[0]
+    b = dict(g["nav_in"])
+    b["vp_img_embeds"] = torch.cat([torch.zeros_like(pano_embeds[:, :1]), pano_embeds], 1)
+    b["pano_masks"] = torch.cat([torch.ones(B, 1, dtype=torch.bool), pano_masks], 1)
+    return b
+
+
+@pytest.mark.parametrize("precision", ["fp32", "amp_bf16"])
+def test_panorama_matches_reference(precision):
+    g, cfg, tok = load(precision)
+    out = O.forward_panorama(g["state_dict"], cfg, **g["pano_in"])
+    for k in ("pano_embeds", "obj_embeds"):
+        assert torch.allclose(out[k], g["pano_out"][k], rtol=2e-5, atol=2e-5), k   # encoder is fp32 in both precisions
+    assert torch.equal(out["pano_masks"], g["pano_out"]["pano_masks"])
+    assert torch.equal(out["obj_masks"], g["pano_out"]["obj_masks"])
+
+
+@pytest.mark.parametrize("precision", ["fp32", "amp_bf16"])
+def test_navigation_forward_and_backward_match_reference(precision):
+    g, cfg, tok = load(precision)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state_dict"].items()}
+    pano = O.forward_panorama(sd, cfg, **g["pano_in"])
+    batch = nav_batch(g, pano["pano_embeds"], pano["pano_masks"])
+    torch.manual_seed(1234)                      # same RNG state as the reference run -> same candidate permutation
+    nav = O.forward_navigation(sd, cfg, batch, tok)
+    ref = g["nav_out"]
+    assert torch.equal(torch.isinf(nav["fuse_logits"]), torch.isinf(ref["fuse_logits"]))
+    fin = ~torch.isinf(ref["fuse_logits"])
+    assert torch.allclose(nav["fuse_logits"][fin].float(), ref["fuse_logits"][fin].float(), **tol(precision))
+    assert torch.allclose(nav["fuse_embeds"], ref["fuse_embeds"], rtol=2e-5, atol=2e-5)
+    loss = F.cross_entropy(nav["fuse_logits"], g["targets"], reduction="sum", ignore_index=-100) / 2
+    assert torch.allclose(loss.float(), ref["loss"].float(), **tol(precision))
+    loss.backward()
+    for name, gr in g["nav_grads"].items():
+        mine = sd[name].grad
+        assert mine is not None, name
+        scale = gr.float().abs().max().item() + 1e-12
+        err = (mine.float() - gr.float()).abs().max().item()
+        lim = 1e-4 if precision == "fp32" else 4e-2
+        assert err <= lim * scale, f"{name}: err {err} vs scale {scale}"
+
+
+@pytest.mark.parametrize("precision", ["fp32", "amp_bf16"])
+def test_object_grounding_matches_reference(precision):
+    g, cfg, tok = load(precision)
+    out = O.forward_object_grounding(g["state_dict"], cfg, g["og_in"], tok)["obj_logits"]
+    ref = g["og_out"]["obj_logits"]
+    assert torch.equal(torch.isinf(out), torch.isinf(ref))
+    fin = ~torch.isinf(ref)
+    assert torch.allclose(out[fin].float(), ref[fin].float(), **tol(precision))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "amp_bf16"])
+def test_lm_loss_modes_match_reference(precision):
+    g, cfg, tok = load(precision)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state_dict"].items()}
+    s = O.forward_summarization(sd, cfg, g["sum_in"], tok, tok.eos_token, training=True)
+    assert torch.allclose(s["loss"].float(), g["sum_out"]["loss"].float(), **tol(precision))
+    s["loss"].backward()
+    for name, gr in g["sum_grads"].items():
+        err = (sd[name].grad.float() - gr.float()).abs().max().item()
+        assert err <= (1e-4 if precision == "fp32" else 4e-2) * (gr.float().abs().max().item() + 1e-12), name
+    sd = {k: v.clone().requires_grad_(v.is_floating_point()) for k, v in g["state_dict"].items()}
+    q = O.forward_3dqa(sd, cfg, g["qa_in"], tok, tok.eos_token, training=True)
+    assert torch.allclose(q["loss"].float(), g["qa_out"]["loss"].float(), **tol(precision))
+    last = q["logits"][:, -1, :]
+    ref = g["qa_out"]["logits_last"]
+    fin = ~torch.isinf(ref)
+    assert torch.equal(torch.isinf(last), torch.isinf(ref))
+    assert torch.allclose(last[fin].float(), ref[fin].float(), **tol(precision))
+    q["loss"].backward()
+    for name, gr in g["qa_grads"].items():
+        err = (sd[name].grad.float() - gr.float()).abs().max().item()
+        assert err <= (1e-4 if precision == "fp32" else 4e-2) * (gr.float().abs().max().item() + 1e-12), name
+
+
+def test_greedy_generate_is_consistent_with_full_forward():
+    """The restated KV-cache greedy loop must produce the tokens a cache-free full re-forward produces
+    (fp32: no near-tie ambiguity at these dims)."""
+    g, cfg, tok = load("fp32")
+    sd = g["state_dict"]
+    qa = g["qa_in"]
+    text = tok(qa["prompts"])
+    feats = qa["features"]
+    lens = torch.tensor([f.shape[0] for f in feats])
+    view = torch.stack([torch.cat([f, f.new_zeros(int(lens.max()) - f.shape[0], f.shape[1])], 0) for f in feats], 0)
+    pano = O.forward_panorama(sd, cfg, view, lens)
+    pe = pano["pano_embeds"] + O._pos_embed(torch.zeros(pano["pano_embeds"].shape[:2] + (14,)), sd, "vp_pos_embeddings")
+    pe = pe + sd["token_type_embeddings.weight"][0]
+    cand = pe[pano["pano_masks"]]
+    ids = O.greedy_generate(sd, cfg, text["input_ids"], text["attention_mask"], cand_vis=cand, max_new_tokens=4,
+                            stop_on_eos=False)
+    cur, mask = text["input_ids"].clone(), text["attention_mask"].clone()
+    for _ in range(4):
+        pos = (mask.cumsum(-1) - 1).masked_fill(mask == 0, 1)
+        out = O.modified_lm_forward(sd, cfg, cur, mask, cand_vis=cand, position_ids=pos)
+        nxt = out["logits"][:, -1].float().argmax(-1)
+        cur = torch.cat([cur, nxt[:, None]], 1)
+        mask = torch.cat([mask, mask.new_ones(2, 1)], 1)
+    assert torch.equal(ids, cur)
