@@ -1,0 +1,268 @@
+"""Packed LLaMA decoder stack over the sm_100a kernels: hand-written forward AND backward.
+
+Host-side mirror of what the reference reaches through ``ModifiedLlamaForCausalLM`` ->
+``transformers.models.llama.LlamaModel`` (reference call site models/modified_lm.py:112-116; HF names kept
+so released checkpoints load: SURVEY.md §5 "checkpoint / resume").  Differences in *how*, not *what*:
+
+* rows are PACKED: only real tokens are computed (the reference pads to the longest prompt and computes the
+  pads); the reference's ``position_ids`` convention is reproduced by explicit per-token positions;
+* q/k/v and gate/up projections run as one GEMM each on fused weight views ([3D,D], [2F,D]);
+* attention never materialises [B,H,S,S];
+* backward is explicit (no autograd graph inside the stack): activations are saved per layer, weight
+  gradients are accumulated in place into a flat bf16 gradient buffer by the wgrad GEMM epilogue.
+
+PyTorch is used for device memory only.  There is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+bf16 = torch.bfloat16
+
+
+@dataclass
+class LlamaDims:
+    hidden: int = 4096
+    n_layers: int = 32
+    n_heads: int = 32
+    inter: int = 11008
+    vocab: int = 32006
+    rms_eps: float = 1e-6
+    rope_theta: float = 10000.0
+    max_pos: int = 4096
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden // self.n_heads
+
+
+class _Linear(nn.Module):
+    """Parameter holder with HF naming (``<name>.weight``); the math lives in the C-ABI kernels."""
+
+    def __init__(self, out_f: int, in_f: int, bias: bool = False, dtype=bf16):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(out_f, in_f, dtype=dtype))
+        self.bias = nn.Parameter(torch.empty(out_f, dtype=dtype)) if bias else None
+
+
+class _Norm(nn.Module):
+    def __init__(self, dim: int, dtype=bf16):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(dim, dtype=dtype))
+
+
+class _Attn(nn.Module):
+    def __init__(self, d: LlamaDims, dtype):
+        super().__init__()
+        self.q_proj = _Linear(d.hidden, d.hidden, dtype=dtype)
+        self.k_proj = _Linear(d.hidden, d.hidden, dtype=dtype)
+        self.v_proj = _Linear(d.hidden, d.hidden, dtype=dtype)
+        self.o_proj = _Linear(d.hidden, d.hidden, dtype=dtype)
+
+
+class _MLP(nn.Module):
+    def __init__(self, d: LlamaDims, dtype):
+        super().__init__()
+        self.gate_proj = _Linear(d.inter, d.hidden, dtype=dtype)
+        self.up_proj = _Linear(d.inter, d.hidden, dtype=dtype)
+        self.down_proj = _Linear(d.hidden, d.inter, dtype=dtype)
+
+
+class _Layer(nn.Module):
+    def __init__(self, d: LlamaDims, dtype):
+        super().__init__()
+        self.self_attn = _Attn(d, dtype)
+        self.mlp = _MLP(d, dtype)
+        self.input_layernorm = _Norm(d.hidden, dtype)
+        self.post_attention_layernorm = _Norm(d.hidden, dtype)
+
+
+class _Embedding(nn.Module):
+    def __init__(self, n: int, dim: int, dtype):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(n, dim, dtype=dtype))
+
+
+class LlamaModelParams(nn.Module):
+    """``model.*`` sub-tree: embed_tokens, layers.N.{self_attn,mlp,input_layernorm,post_attention_layernorm}, norm."""
+
+    def __init__(self, d: LlamaDims, dtype=bf16):
+        super().__init__()
+        self.embed_tokens = _Embedding(d.vocab, d.hidden, dtype)
+        self.layers = nn.ModuleList([_Layer(d, dtype) for _ in range(d.n_layers)])
+        self.norm = _Norm(d.hidden, dtype)
+
+
+def init_llama_params_(model: LlamaModelParams, lm_head: _Linear, std: float = 0.02, seed: int = 0) -> None:
+    """HF default init (normal(0, 0.02) for linears/embeddings, ones for RMSNorm), generated on the host."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in list(model.parameters()) + list(lm_head.parameters()):
+            if p.dim() == 1:
+                p.fill_(1.0)
+            else:
+                # chunked so a 7B init never holds more than one fp32 matrix on the host
+                p.copy_((torch.randn(p.shape, generator=g) * std).to(p.dtype))
+
+
+class FlatParams:
+    """Re-homes a list of same-dtype parameters into ONE contiguous buffer (and one gradient buffer).
+
+    q/k/v and gate/up of a layer become adjacent row blocks, so the fused [3D,D] / [2F,D] weights are plain
+    views; ``p.grad`` of every parameter is a view of the flat gradient buffer, so data-parallel reduction is a
+    single NCCL all-reduce over ``flat_grad`` and the optimizer sees ordinary ``.grad``s.
+    """
+
+    def __init__(self, params: List[nn.Parameter], device: torch.device):
+        assert params and all(p.dtype == params[0].dtype for p in params)
+        self.params = params
+        self.dtype = params[0].dtype
+        align = 64  # elements; keeps every view 128-byte aligned for TMA / vector access
+        offs, total = [], 0
+        for p in params:
+            offs.append(total)
+            total += (p.numel() + align - 1) // align * align
+        self.offsets = offs
+        self.flat = torch.empty(total, dtype=self.dtype, device=device)
+        self.flat_grad = torch.zeros(total, dtype=self.dtype, device=device)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                view = self.flat[o:o + p.numel()].view(p.shape)
+                view.copy_(p.data.to(device))
+                p.data = view
+                p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        self._ptr0 = params[0].data_ptr()
+
+    def intact(self) -> bool:
+        return self.params[0].data_ptr() == self._ptr0 and self.params[0].grad is not None and \
+            self.params[0].grad.data_ptr() == self.flat_grad.data_ptr()
+
+    def reattach_grads(self) -> None:
+        """After ``optimizer.zero_grad(set_to_none=True)``: zero the buffer and hand the views back."""
+        self.flat_grad.zero_()
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
+    def view(self, first: nn.Parameter, n_params: int, shape) -> torch.Tensor:
+        i = next(k for k, p in enumerate(self.params) if p is first)
+        o = self.offsets[i]
+        numel = 1
+        for s in shape:
+            numel *= s
+        # adjacency holds only if the fused members are unpadded multiples of the alignment
+        assert self.offsets[i + n_params - 1] + self.params[i + n_params - 1].numel() - o == numel, "fused view not contiguous"
+        return self.flat[o:o + numel].view(shape)
+
+    def grad_view(self, first: nn.Parameter, n_params: int, shape) -> torch.Tensor:
+        i = next(k for k, p in enumerate(self.params) if p is first)
+        o = self.offsets[i]
+        numel = 1
+        for s in shape:
+            numel *= s
+        return self.flat_grad[o:o + numel].view(shape)
+
+
+def rope_tables(d: LlamaDims, device) -> tuple:
+    """cos/sin [max_pos, head_dim] in bf16, built exactly like HF LlamaRotaryEmbedding (fp32 cos/sin of
+    pos * inv_freq, concatenated halves, cast to the model dtype)."""
+    hd = d.head_dim
+    inv = 1.0 / (d.rope_theta ** (torch.arange(0, hd, 2, dtype=torch.int64).float() / hd))
+    fr = torch.arange(d.max_pos, dtype=torch.float32)[:, None] * inv[None, :]
+    emb = torch.cat([fr, fr], dim=-1)
+    return emb.cos().to(bf16).to(device).contiguous(), emb.sin().to(bf16).to(device).contiguous()
+
+
+class _Saved:
+    __slots__ = ("x", "rstd1", "xn", "qkv", "ao", "lse", "xm", "rstd2", "xn2", "gu", "h")
+
+
+class LlamaCore:
+    """Forward/backward driver of the decoder stack on packed rows.  Not an nn.Module: parameters live in
+    ``LlamaModelParams`` (HF-named) and are accessed through fused views of a ``FlatParams`` buffer."""
+
+    def __init__(self, dims: LlamaDims, model: LlamaModelParams, flat: FlatParams):
+        self.d = dims
+        self.model = model
+        self.flat = flat
+        D, F = dims.hidden, dims.inter
+        self.wqkv, self.gqkv, self.wo, self.go, self.wgu, self.ggu, self.wd, self.gd = [], [], [], [], [], [], [], []
+        for lyr in model.layers:
+            a, m = lyr.self_attn, lyr.mlp
+            self.wqkv.append(flat.view(a.q_proj.weight, 3, (3 * D, D)))
+            self.gqkv.append(flat.grad_view(a.q_proj.weight, 3, (3 * D, D)))
+            self.wo.append(a.o_proj.weight.data)
+            self.go.append(a.o_proj.weight.grad)
+            self.wgu.append(flat.view(m.gate_proj.weight, 2, (2 * F, D)))
+            self.ggu.append(flat.grad_view(m.gate_proj.weight, 2, (2 * F, D)))
+            self.wd.append(m.down_proj.weight.data)
+            self.gd.append(m.down_proj.weight.grad)
+        self.cos, self.sin = rope_tables(dims, flat.flat.device)
+        self.saved: List[_Saved] = []
+        self.meta = None
+
+    # -------------------------------------------------------------------------------------------------
+    def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True) -> torch.Tensor:
+        """x: [T, D] bf16 input embeddings (packed); pos: int32 [T]; cu: int32 [B+1] (device); seqlens: host
+        lengths.  Returns the residual stream after the last layer, BEFORE the final RMSNorm."""
+        d = self.d
+        H = d.n_heads
+        self.saved = []
+        self.meta = (pos, cu, list(seqlens))
+        for l, lyr in enumerate(self.model.layers):
+            s = _Saved()
+            s.x = x
+            s.xn, s.rstd1 = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
+            s.qkv = ops.gemm(s.xn, self.wqkv[l])
+            ops.rope_(s.qkv, pos, self.cos, self.sin, 2 * H, d.head_dim)
+            s.ao, s.lse = ops.attn_fwd(s.qkv, cu, seqlens, H)
+            s.xm = ops.gemm(s.ao, self.wo[l], addend=x)
+            s.xn2, s.rstd2 = ops.rmsnorm_fwd(s.xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
+            s.gu = ops.gemm(s.xn2, self.wgu[l])
+            s.h = ops.swiglu_fwd(s.gu)
+            x = ops.gemm(s.h, self.wd[l], addend=s.xm)
+            if save:
+                self.saved.append(s)
+        return x
+
+    # -------------------------------------------------------------------------------------------------
+    def backward(self, dx: torch.Tensor) -> torch.Tensor:
+        """dx: [T, D] bf16 gradient w.r.t. the forward's return value.  Accumulates every weight gradient
+        in place and returns the gradient w.r.t. the input embeddings."""
+        assert self.saved, "LlamaCore.backward without a saved forward"
+        d = self.d
+        H = d.n_heads
+        pos, cu, seqlens = self.meta
+        for l in range(d.n_layers - 1, -1, -1):
+            lyr, s = self.model.layers[l], self.saved[l]
+            # ---- MLP:  x_out = xm + down(swiglu(gate_up(rmsnorm2(xm)))) ----
+            dh = ops.gemm(dx, self.wd[l], b_mn=True)                                   # [T,F]  dgrad
+            ops.gemm(dx, s.h, a_mn=True, b_mn=True, out=self.gd[l], addend=self.gd[l])  # dWd += dx^T h
+            dgu = ops.swiglu_bwd(s.gu, dh)
+            del dh
+            dxn2 = ops.gemm(dgu, self.wgu[l], b_mn=True)                               # [T,D]
+            ops.gemm(dgu, s.xn2, a_mn=True, b_mn=True, out=self.ggu[l], addend=self.ggu[l])
+            del dgu
+            dxm = ops.rmsnorm_bwd(s.xm, lyr.post_attention_layernorm.weight.data, s.rstd2, dxn2, dres=dx,
+                                  dw=lyr.post_attention_layernorm.weight.grad)
+            del dxn2
+            # ---- attention:  xm = x + o_proj(attn(rope(qkv(rmsnorm1(x))))) ----
+            dao = ops.gemm(dxm, self.wo[l], b_mn=True)
+            ops.gemm(dxm, s.ao, a_mn=True, b_mn=True, out=self.go[l], addend=self.go[l])
+            dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H)
+            del dao
+            ops.rope_(dqkv, pos, self.cos, self.sin, 2 * H, d.head_dim, backward=True)
+            dxn = ops.gemm(dqkv, self.wqkv[l], b_mn=True)
+            ops.gemm(dqkv, s.xn, a_mn=True, b_mn=True, out=self.gqkv[l], addend=self.gqkv[l])
+            del dqkv
+            dx = ops.rmsnorm_bwd(s.x, lyr.input_layernorm.weight.data, s.rstd1, dxn, dres=dxm,
+                                 dw=lyr.input_layernorm.weight.grad)
+            del dxn, dxm
+            self.saved[l] = None
+        self.saved = []
+        return dx
