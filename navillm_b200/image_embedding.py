@@ -1,0 +1,237 @@
+"""Panorama scene encoder on the fp32 sm_100a kernels (csrc/pano_ops.cu), forward + hand-written backward.
+
+Mirror of the reference's ``ImageEmbeddings`` (models/image_embedding.py:11-121) with the DETR pre-LN encoder
+(models/detr_transformer.py:62-89,170-182; built by models/ops.py:6-18): same constructor arguments, same
+parameter names/shapes (``img_linear``, ``img_layer_norm``, ``loc_linear``, ``loc_layer_norm``,
+``obj_projector.{0,1}``, ``nav_type_embedding``, ``layer_norm``, ``pano_encoder.layers.N.{self_attn.in_proj_weight,
+in_proj_bias,self_attn.out_proj,linear1,linear2,norm1,norm2}``, ``pano_encoder.norm``, ``mapper``) so reference
+checkpoints load.  The torch.nn modules below are parameter holders (and give the reference's default
+initialisation); their ``forward`` is never called -- all arithmetic runs in the C-ABI kernels.
+
+Round-1 scope note: the encoder-internal dropouts (p=0.1, active only in ``train()``) are not applied;
+parity is defined in ``eval()``.  ``fuse_obj`` (off in every reference config) is unsupported.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+f32 = torch.float32
+
+
+class _EncoderLayer(nn.Module):
+    def __init__(self, d_model, nhead, dim_ff):
+        super().__init__()
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=0.1)
+        self.linear1 = nn.Linear(d_model, dim_ff)
+        self.linear2 = nn.Linear(dim_ff, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+
+class _Encoder(nn.Module):
+    def __init__(self, d_model, nhead, dim_ff, num_layers):
+        super().__init__()
+        self.layers = nn.ModuleList([_EncoderLayer(d_model, nhead, dim_ff) for _ in range(num_layers)])
+        self.norm = nn.LayerNorm(d_model, eps=1e-12)
+
+
+def _grad(p: torch.Tensor) -> torch.Tensor:
+    if p.grad is None:
+        p.grad = torch.zeros_like(p)
+    return p.grad
+
+
+def _lin_fwd(x, lin: nn.Linear, out=None, accumulate=False):
+    return ops.sgemm(x, lin.weight.data, bias=lin.bias.data if lin.bias is not None else None, out=out,
+                     accumulate=accumulate)
+
+
+def _lin_bwd(dy, x, lin: nn.Linear, need_dx=True):
+    """dW += dy^T x ; db += colsum(dy) ; returns dx = dy W."""
+    ops.sgemm(dy, x, ta=True, tb=True, out=_grad(lin.weight), accumulate=True)
+    if lin.bias is not None:
+        ops.colsum_(dy, _grad(lin.bias), accumulate=True)
+    return ops.sgemm(dy, lin.weight.data, tb=True) if need_dx else None
+
+
+def _ln_fwd(x, ln: nn.LayerNorm, addend=None):
+    return ops.layernorm_fwd(x, ln.weight.data, ln.bias.data, ln.eps, addend=addend)
+
+
+def _ln_bwd(dy, x, ln: nn.LayerNorm, mean, rstd, dx=None, accumulate_dx=False):
+    return ops.layernorm_bwd(x, ln.weight.data, mean, rstd, dy, dx=dx, accumulate_dx=accumulate_dx,
+                             dgamma=_grad(ln.weight), dbeta=_grad(ln.bias))
+
+
+class _PanoFn(torch.autograd.Function):
+    """Differentiable boundary of the encoder: the outputs carry grad_fn so the caller's loss.backward()
+    reaches ``backward`` below, which accumulates every parameter gradient natively."""
+
+    @staticmethod
+    def forward(ctx, mod: "ImageEmbeddings", view, lens32, loc, types32, keep_idx, anchor):
+        B, N, Dv = view.shape
+        R = B * N
+        v2 = view.reshape(R, Dv)
+        t = {}
+        t["v2"] = v2
+        t["ximg"] = _lin_fwd(v2, mod.img_linear)
+        a, t["m_img"], t["r_img"] = _ln_fwd(t["ximg"], mod.img_layer_norm)
+        t["loc2"] = loc.reshape(R, loc.shape[-1])
+        t["xloc"] = _lin_fwd(t["loc2"], mod.loc_linear)
+        c, t["m_loc"], t["r_loc"] = _ln_fwd(t["xloc"], mod.loc_layer_norm, addend=a)
+        ops.rows_combine(c, b=mod.nav_type_embedding.weight.data, ib=types32, accumulate=True)
+        t["c"] = c
+        x, t["m_ln"], t["r_ln"] = _ln_fwd(c, mod.layer_norm)
+        layers = []
+        enc = mod.pano_encoder
+        if enc is not None:
+            for lyr in enc.layers:
+                s = {"x": x}
+                s["h"], s["m1"], s["r1"] = _ln_fwd(x, lyr.norm1)
+                s["qkv"] = ops.sgemm(s["h"], lyr.self_attn.in_proj_weight.data, bias=lyr.self_attn.in_proj_bias.data)
+                att, s["P"] = ops.mha_fwd(s["qkv"].view(B, N, -1), lens32, mod.num_heads)
+                s["att"] = att.view(R, -1)
+                x1 = x.clone()
+                _lin_fwd(s["att"], lyr.self_attn.out_proj, out=x1, accumulate=True)
+                s["x1"] = x1
+                s["h2"], s["m2"], s["r2"] = _ln_fwd(x1, lyr.norm2)
+                s["z"] = _lin_fwd(s["h2"], lyr.linear1)
+                s["a1"] = ops.gelu_fwd(s["z"])
+                x2 = x1.clone()
+                _lin_fwd(s["a1"], lyr.linear2, out=x2, accumulate=True)
+                x = x2
+                layers.append(s)
+            t["xe"] = x
+            x, t["m_f"], t["r_f"] = _ln_fwd(x, enc.norm)
+        t["y"] = x
+        m = _lin_fwd(x, mod.mapper)
+        out = torch.empty_like(m)
+        ops.rows_combine(out, a=m, ia=keep_idx)       # zero the padded rows (image_embedding.py:103)
+        ctx.mod, ctx.t, ctx.layers = mod, t, layers
+        ctx.dims = (B, N)
+        ctx.lens32, ctx.types32, ctx.keep_idx = lens32, types32, keep_idx
+        return out.view(B, N, -1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        mod, t, layers = ctx.mod, ctx.t, ctx.layers
+        B, N = ctx.dims
+        R = B * N
+        dout = dout.contiguous().view(R, -1).to(f32)
+        dm = torch.empty_like(dout)
+        ops.rows_combine(dm, a=dout, ia=ctx.keep_idx)               # padded rows carry no gradient
+        dx = _lin_bwd(dm, t["y"], mod.mapper)
+        enc = mod.pano_encoder
+        if enc is not None:
+            dx = _ln_bwd(dx, t["xe"], enc.norm, t["m_f"], t["r_f"])
+            for lyr, s in zip(reversed(list(enc.layers)), reversed(layers)):
+                da1 = _lin_bwd(dx, s["a1"], lyr.linear2)
+                dz = ops.gelu_bwd(s["z"], da1)
+                dh2 = _lin_bwd(dz, s["h2"], lyr.linear1)
+                dx1 = dx.clone()
+                _ln_bwd(dh2, s["x1"], lyr.norm2, s["m2"], s["r2"], dx=dx1, accumulate_dx=True)
+                datt = _lin_bwd(dx1, s["att"], lyr.self_attn.out_proj)
+                dqkv = ops.mha_bwd(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], ctx.lens32, mod.num_heads).view(R, -1)
+                sa = lyr.self_attn
+                ops.sgemm(dqkv, s["h"], ta=True, tb=True, out=_grad(sa.in_proj_weight), accumulate=True)
+                ops.colsum_(dqkv, _grad(sa.in_proj_bias), accumulate=True)
+                dh = ops.sgemm(dqkv, sa.in_proj_weight.data, tb=True)
+                dx = dx1
+                _ln_bwd(dh, s["x"], lyr.norm1, s["m1"], s["r1"], dx=dx, accumulate_dx=True)
+        dc = _ln_bwd(dx, t["c"], mod.layer_norm, t["m_ln"], t["r_ln"])
+        ops.rows_scatter_add_(_grad(mod.nav_type_embedding.weight), ctx.types32, dc)
+        dxloc = _ln_bwd(dc, t["xloc"], mod.loc_layer_norm, t["m_loc"], t["r_loc"])
+        _lin_bwd(dxloc, t["loc2"], mod.loc_linear, need_dx=False)
+        dximg = _ln_bwd(dc, t["ximg"], mod.img_layer_norm, t["m_img"], t["r_img"])
+        _lin_bwd(dximg, t["v2"], mod.img_linear, need_dx=False)
+        ctx.t = ctx.layers = None
+        return None, None, None, None, None, None, None
+
+
+class _ObjFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mod: "ImageEmbeddings", obj, anchor):
+        B, O, Do = obj.shape
+        o2 = obj.reshape(B * O, Do)
+        x = _lin_fwd(o2, mod.obj_projector[0])
+        y, mean, rstd = _ln_fwd(x, mod.obj_projector[1])
+        ctx.mod, ctx.saved = mod, (o2, x, mean, rstd)
+        return y.view(B, O, -1)
+
+    @staticmethod
+    def backward(ctx, dy):
+        mod = ctx.mod
+        o2, x, mean, rstd = ctx.saved
+        dy = dy.contiguous().view(x.shape[0], -1).to(f32)
+        dx = _ln_bwd(dy, x, mod.obj_projector[1], mean, rstd)
+        _lin_bwd(dx, o2, mod.obj_projector[0], need_dx=False)
+        return None, None, None
+
+
+def gen_seq_masks(seq_lens: torch.Tensor, max_len=None) -> torch.Tensor:
+    """models/ops.py:33-41 (max over lens is a host value: lens arrive from the host in the agent)."""
+    if max_len is None:
+        max_len = int(seq_lens.max())
+    return torch.arange(max_len, device=seq_lens.device).unsqueeze(0) < seq_lens.unsqueeze(1)
+
+
+class ImageEmbeddings(nn.Module):
+    def __init__(self, config, use_obj: bool = False, fuse_obj: bool = False):
+        super().__init__()
+        if fuse_obj:
+            raise NotImplementedError("fuse_obj=True is off in every reference config and not built (round 1)")
+        H = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.img_linear = nn.Linear(config.image_feat_size, H)
+        self.img_layer_norm = nn.LayerNorm(H, eps=1e-12)
+        self.loc_linear = nn.Linear(config.angle_feat_size + 3, H)
+        self.loc_layer_norm = nn.LayerNorm(H, eps=1e-12)
+        self.fuse_obj = fuse_obj
+        if use_obj:
+            self.obj_projector = nn.Sequential(nn.Linear(config.obj_feat_size, config.output_size),
+                                               nn.LayerNorm(config.output_size, eps=1e-12))
+        else:
+            self.obj_projector = None
+        self.nav_type_embedding = nn.Embedding(3, H)
+        self.layer_norm = nn.LayerNorm(H, eps=1e-12)
+        self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        if config.num_pano_layers > 0:
+            self.pano_encoder = _Encoder(H, config.num_attention_heads, config.intermediate_size, config.num_pano_layers)
+        else:
+            self.pano_encoder = None
+        self.mapper = nn.Linear(H, config.output_size)
+        # autograd anchor: a 0-d tensor that requires grad so the Function's outputs get a grad_fn even
+        # though no *input tensor* of the encoder needs a gradient (parameters are updated natively)
+        self.register_buffer("_anchor", torch.zeros((), dtype=f32), persistent=False)
+
+    def forward_panorama_per_step(self, view_img_fts, view_lens, loc_fts=None, nav_types=None, obj_img_fts=None,
+                                  obj_lens=None, obj_loc_fts=None):
+        """Same contract as the reference (models/image_embedding.py:51-121)."""
+        if not view_img_fts.is_cuda:
+            raise RuntimeError("navillm_b200 has no CPU path: inputs must be CUDA tensors")
+        dev = view_img_fts.device
+        B, N = view_img_fts.shape[:2]
+        view = view_img_fts.to(f32).contiguous()
+        if loc_fts is None:
+            loc_fts = torch.zeros((B, N, 7), dtype=f32, device=dev)
+        if nav_types is None:
+            nav_types = torch.ones((B, N), dtype=torch.int32, device=dev)
+        lens32 = view_lens.to(device=dev, dtype=torch.int32)
+        pano_masks = gen_seq_masks(view_lens.to(dev), N)
+        rows = torch.arange(B * N, device=dev, dtype=torch.int32)
+        keep_idx = torch.where(pano_masks.reshape(-1), rows, torch.full_like(rows, -1))
+        anchor = self._anchor.detach().requires_grad_(torch.is_grad_enabled())
+        pano = _PanoFn.apply(self, view, lens32, loc_fts.to(f32).contiguous(), nav_types.to(torch.int32).reshape(-1).contiguous(),
+                             keep_idx, anchor)
+        ret = {"pano_embeds": pano, "pano_masks": pano_masks}
+        if obj_img_fts is not None and obj_img_fts.shape[1] > 0:
+            assert self.obj_projector is not None, "object features given but the model was built with enable_og=False"
+            obj = _ObjFn.apply(self, obj_img_fts.to(f32).contiguous(), anchor)
+            obj_masks = gen_seq_masks(obj_lens.to(dev), obj_img_fts.shape[1])
+            assert obj.shape[:2] == obj_loc_fts.shape[:2], \
+                f"shape of obj_embeds {obj.shape[:2]} must equal to shape of obj_loc_fts {obj_loc_fts.shape[:2]}"
+            ret.update({"obj_embeds": obj, "obj_loc_fts": obj_loc_fts, "obj_masks": obj_masks})
+        return ret

@@ -251,3 +251,116 @@ def attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Te
                                   i32(T), i32(n_heads), i32(hd), i32(_qblocks(seqlens)), f32(scale), stream_ptr()),
           "nv_attn_bwd")
     return dqkv
+
+
+# ---------------------------------------------------------------------------------------------------
+# fp32 panorama-encoder / fusion kernels (csrc/pano_ops.cu)
+# ---------------------------------------------------------------------------------------------------
+f32_t = torch.float32
+
+
+def _f32_2d(t: torch.Tensor, name: str) -> None:
+    if t.dtype != f32_t or t.dim() != 2 or t.stride(1) != 1 or not t.is_cuda:
+        raise ValueError(f"{name}: expected a 2-D fp32 CUDA tensor with unit inner stride, got {t.dtype} {tuple(t.shape)} {t.stride()}")
+
+
+def sgemm(a, b, *, ta=False, tb=False, bias=None, out=None, accumulate=False):
+    """C = op(A)·op(B) (+bias).  a: [M,K] (ta=False) / [K,M];  b: [N,K] (tb=False, nn.Linear weight) / [K,N]."""
+    _f32_2d(a, "a"); _f32_2d(b, "b")
+    M, K = (a.shape[1], a.shape[0]) if ta else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if tb else b.shape
+    assert K == Kb, f"sgemm contraction mismatch {K} vs {Kb}"
+    if out is None:
+        assert not accumulate
+        out = torch.empty((M, N), dtype=f32_t, device=a.device)
+    _f32_2d(out, "out")
+    check(_lib.load().nv_sgemm(ptr(a), i64(a.stride(0)), i32(ta), ptr(b), i64(b.stride(0)), i32(tb), ptr(out),
+                               i64(out.stride(0)), ptr(bias), i32(M), i32(N), i32(K), i32(accumulate), stream_ptr()),
+          "nv_sgemm")
+    return out
+
+
+def layernorm_fwd(x, gamma, beta, eps, *, addend=None, out=None, save_stats=True):
+    _f32_2d(x, "x")
+    R, D = x.shape
+    if out is None:
+        out = torch.empty((R, D), dtype=f32_t, device=x.device)
+    mean = torch.empty((R,), dtype=f32_t, device=x.device) if save_stats else None
+    rstd = torch.empty((R,), dtype=f32_t, device=x.device) if save_stats else None
+    check(_lib.load().nv_layernorm_fwd(ptr(x), i64(x.stride(0)), ptr(gamma), ptr(beta), ptr(addend),
+                                       i64(addend.stride(0) if addend is not None else 0), ptr(out), i64(out.stride(0)),
+                                       ptr(mean), ptr(rstd), i32(R), i32(D), f32(eps), stream_ptr()), "nv_layernorm_fwd")
+    return out, mean, rstd
+
+
+def layernorm_bwd(x, gamma, mean, rstd, dy, *, dx=None, accumulate_dx=False, dgamma=None, dbeta=None):
+    _f32_2d(x, "x"); _f32_2d(dy, "dy")
+    R, D = x.shape
+    lib = _lib.load()
+    if dx is None:
+        assert not accumulate_dx
+        dx = torch.empty((R, D), dtype=f32_t, device=x.device)
+    ws = _workspace(x.device, lib.nv_layernorm_bwd_partials() * 2 * D)
+    check(lib.nv_layernorm_bwd(ptr(x), i64(x.stride(0)), ptr(gamma), ptr(mean), ptr(rstd), ptr(dy), i64(dy.stride(0)),
+                               ptr(dx), i64(dx.stride(0)), i32(accumulate_dx), ptr(dgamma), ptr(dbeta), ptr(ws), i32(R),
+                               i32(D), stream_ptr()), "nv_layernorm_bwd")
+    return dx
+
+
+def colsum_(src, dst, accumulate=True):
+    _f32_2d(src, "src")
+    check(_lib.load().nv_colsum_f32(ptr(src), i64(src.stride(0)), i32(src.shape[0]), i32(src.shape[1]), ptr(dst),
+                                    i32(accumulate), stream_ptr()), "nv_colsum_f32")
+    return dst
+
+
+def gelu_fwd(z):
+    a = torch.empty_like(z)
+    check(_lib.load().nv_gelu_fwd(ptr(z), ptr(a), i64(z.numel()), stream_ptr()), "nv_gelu_fwd")
+    return a
+
+
+def gelu_bwd(z, da):
+    dz = torch.empty_like(z)
+    check(_lib.load().nv_gelu_bwd(ptr(z), ptr(da), ptr(dz), i64(z.numel()), stream_ptr()), "nv_gelu_bwd")
+    return dz
+
+
+def mha_fwd(qkv, lens, n_heads, *, save_probs=True):
+    """qkv: [B, N, 3E] fp32 contiguous; lens: int32 [B].  Returns (out [B,N,E], P [B,H,N,N] or None)."""
+    B, N, E3 = qkv.shape
+    E = E3 // 3
+    assert qkv.is_contiguous() and qkv.dtype == f32_t and lens.dtype == torch.int32
+    out = torch.empty((B, N, E), dtype=f32_t, device=qkv.device)
+    P = torch.empty((B, n_heads, N, N), dtype=f32_t, device=qkv.device) if save_probs else None
+    check(_lib.load().nv_mha_fwd(ptr(qkv), ptr(lens), ptr(out), ptr(P), i32(B), i32(N), i32(n_heads), i32(E // n_heads),
+                                 stream_ptr()), "nv_mha_fwd")
+    return out, P
+
+
+def mha_bwd(qkv, dout, P, lens, n_heads):
+    B, N, E3 = qkv.shape
+    E = E3 // 3
+    assert dout.is_contiguous() and P.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    dS = torch.empty_like(P)
+    check(_lib.load().nv_mha_bwd(ptr(qkv), ptr(dout), ptr(P), ptr(dS), ptr(dqkv), ptr(lens), i32(B), i32(N), i32(n_heads),
+                                 i32(E // n_heads), stream_ptr()), "nv_mha_bwd")
+    return dqkv
+
+
+def rows_combine(out, a=None, ia=None, alpha=1.0, b=None, ib=None, beta=1.0, accumulate=False):
+    """out[r] = (accumulate ? out[r] : 0) + alpha*a[ia[r]] + beta*b[ib[r]]  (index < 0 -> nothing; ia None -> r)."""
+    _f32_2d(out, "out")
+    R, D = out.shape
+    check(_lib.load().nv_rows_combine(ptr(out), i64(out.stride(0)), ptr(a), i64(a.stride(0) if a is not None else 0), ptr(ia),
+                                      f32(alpha), ptr(b), i64(b.stride(0) if b is not None else 0), ptr(ib), f32(beta),
+                                      i32(R), i32(D), i32(accumulate), stream_ptr()), "nv_rows_combine")
+    return out
+
+
+def rows_scatter_add_(dst, idx, src, alpha=1.0):
+    _f32_2d(dst, "dst"); _f32_2d(src, "src")
+    check(_lib.load().nv_rows_scatter_add(ptr(dst), i64(dst.stride(0)), ptr(idx), ptr(src), i64(src.stride(0)), f32(alpha),
+                                          i32(src.shape[0]), i32(src.shape[1]), stream_ptr()), "nv_rows_scatter_add")
+    return dst
