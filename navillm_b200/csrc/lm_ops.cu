@@ -461,6 +461,25 @@ __global__ void __launch_bounds__(256) ce_kernel(const __nv_bfloat16* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Action-logit scatter (models/nav_model.py:234-242): out[b,g] = slot[b,g] >= 0 ? pred[b, slot[b,g]] : -inf
+// and its transpose for the gradient (each prediction column feeds at most one slot).
+// ------------------------------------------------------------------------------------------------
+__global__ void logit_scatter_fwd_kernel(const __nv_bfloat16* __restrict__ pred, int O, const int* __restrict__ slot,
+                                         __nv_bfloat16* __restrict__ out, int B, int G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  const int s = slot[i];
+  out[i] = s >= 0 ? pred[(i / G) * O + s] : __float2bfloat16_rn(-INFINITY);
+}
+__global__ void logit_scatter_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int* __restrict__ slot,
+                                         __nv_bfloat16* __restrict__ dpred, int O, int B, int G) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * G) return;
+  const int s = slot[i];
+  if (s >= 0) dpred[(i / G) * O + s] = dout[i];
+}
+
 static inline int grid_for(int64_t work, int block, int cap_mult = 8) {
   int64_t g = (work + block - 1) / block;
   const int64_t cap = (int64_t)sm_count() * cap_mult;
@@ -602,6 +621,21 @@ int nv_ce_fwd_bwd(const void* logits, int64_t ld, const int* labels, const int* 
   if (N == 0) return NV_OK;
   NV_REQUIRE(n_special >= 0 && n_special <= 16, "nv_ce_fwd_bwd: n_special out of range");
   ce_kernel<<<N, 256, 0, S_(stream)>>>(CBF(logits), ld, labels, special, n_special, row_loss, BF(dlogits), ldd, V, grad_scale);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_logit_scatter_fwd(const void* pred, int O, const int* slot, void* out, int B, int G, void* stream) {
+  if (B * G == 0) return NV_OK;
+  logit_scatter_fwd_kernel<<<(B * G + 127) / 128, 128, 0, S_(stream)>>>(CBF(pred), O, slot, BF(out), B, G);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+// dpred must be zero-initialised by the caller
+int nv_logit_scatter_bwd(const void* dout, const int* slot, void* dpred, int O, int B, int G, void* stream) {
+  if (B * G == 0) return NV_OK;
+  logit_scatter_bwd_kernel<<<(B * G + 127) / 128, 128, 0, S_(stream)>>>(CBF(dout), slot, BF(dpred), O, B, G);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -1,0 +1,304 @@
+"""Modified LLaMA causal LM on the sm_100a kernels -- host mirror of the reference's
+``ModifiedLlamaForCausalLM`` (models/modified_lm.py:33-146,176-199).
+
+Same surface: ``init_tokenizer``, ``tokenize``, ``forward(input_ids, attention_mask, labels, cand_vis, hist_vis,
+obj_vis)`` returning an object with ``loss / logits / hidden_states``, ``generate`` (greedy / sampling),
+attributes ``tokenizer, cls_token, cand_token_id, hist_token_id, obj_token_id, cls_token_id, special_token_ids,
+hidden_size, model_type`` and HF parameter names ``model.embed_tokens / model.layers.N.* / model.norm / lm_head``.
+
+What differs is the execution (see llama.py): prompts are packed (pad tokens are never computed), the visual
+scatter-add is fused with the embedding gather, ``lm_head`` runs only on rows whose logits are consumed
+(reference computes [B,S,V] logits + a [B,S,V] bool mask in every mode: SURVEY.md Appendix A.10), and the
+backward is hand-written.  ``hidden_states`` / ``logits`` at pad positions are zeros / absent here, where the
+reference holds values computed from pad embeddings that nothing reads.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .llama import FlatParams, LlamaCore, LlamaDims, LlamaModelParams, _Linear, init_llama_params_
+from .tokenizer import SPECIAL_TOKENS, HFTokenizerAdapter, SyntheticTokenizer
+
+bf16 = torch.bfloat16
+
+
+class LMOutput(SimpleNamespace):
+    """Stand-in for transformers.CausalLMOutputWithPast (attribute and item access)."""
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+
+class PackedPrompt:
+    """Host-side packing of a left-padded [B,S] prompt batch: everything the kernels need, built with numpy
+    on the tokenizer's CPU tensors and shipped to the device in ONE int32 copy."""
+
+    def __init__(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, lm: "ModifiedLlamaForCausalLM",
+                 device: torch.device, labels: Optional[torch.Tensor] = None, generate_positions: bool = False):
+        ids = input_ids.detach().cpu().numpy().astype(np.int64)
+        msk = attention_mask.detach().cpu().numpy().astype(bool)
+        B, S = ids.shape
+        self.B, self.S = B, S
+        self.seqlens = msk.sum(1).astype(np.int64).tolist()
+        flat_rows = np.flatnonzero(msk.reshape(-1))                       # packed order == row-major order
+        self.T = int(flat_rows.size)
+        tok = ids.reshape(-1)[flat_rows]
+        if generate_positions:                                            # HF generate: cumsum(mask) - 1
+            pos = (np.cumsum(msk, axis=1) - 1).reshape(-1)[flat_rows]
+        else:                                                             # plain forward: arange(S), pads included
+            pos = np.tile(np.arange(S), B)[flat_rows]
+        cu = np.concatenate([[0], np.cumsum(self.seqlens)])
+        # visual scatter map: row-major order of each token kind (models/modified_lm.py:100-110); the vis tensor
+        # handed to the kernel is cat([cand_vis, hist_vis, obj_vis])
+        is_c, is_h, is_o = tok == lm.cand_token_id[0], tok == lm.hist_token_id[0], tok == lm.obj_token_id[0]
+        self.n_cand, self.n_hist, self.n_obj = int(is_c.sum()), int(is_h.sum()), int(is_o.sum())
+        vis_src = np.full(self.T, -1, dtype=np.int64)
+        vis_src[is_c] = np.arange(self.n_cand)
+        vis_src[is_h] = self.n_cand + np.arange(self.n_hist)
+        vis_src[is_o] = self.n_cand + self.n_hist + np.arange(self.n_obj)
+        # <cls_1> rows (one per sequence is assumed by the reference: nav_model.py:237)
+        cls_rows = np.flatnonzero(tok == lm.cls_token_id[0])
+        # last real token of every sequence (decode)
+        last_rows = cu[1:] - 1
+        # LM-loss rows: position p predicts token p+1 (shifted CE, modified_lm.py:126-137)
+        if labels is not None:
+            lab = labels.detach().cpu().numpy().astype(np.int64)
+            nxt = np.full((B, S), -100, dtype=np.int64)
+            nxt[:, :-1] = lab[:, 1:]
+            nxt_packed = nxt.reshape(-1)[flat_rows]
+            loss_rows = np.flatnonzero(nxt_packed != -100)
+            loss_tgt = nxt_packed[loss_rows]
+        else:
+            loss_rows = np.zeros(0, dtype=np.int64)
+            loss_tgt = np.zeros(0, dtype=np.int64)
+        self.n_cls, self.n_loss = int(cls_rows.size), int(loss_rows.size)
+        parts = [tok, pos, cu, vis_src, cls_rows, last_rows, loss_rows, loss_tgt]
+        host = np.concatenate([p.astype(np.int32) for p in parts])
+        buf = torch.from_numpy(host).pin_memory() if torch.cuda.is_available() else torch.from_numpy(host)
+        dev = buf.to(device, non_blocking=True)
+        self.h2d_bytes = host.nbytes
+        o = 0
+        views = []
+        for p in parts:
+            views.append(dev[o:o + p.size])
+            o += p.size
+        (self.ids, self.pos, self.cu, self.vis_src, self.cls_rows, self.last_rows, self.loss_rows, self.loss_tgt) = views
+        self.flat_rows = flat_rows                                        # host copy (unpacking to [B,S])
+
+
+class _LMFn(torch.autograd.Function):
+    """Differentiable boundary of the language model for a packed prompt.
+
+    inputs : vis [Nv, D] fp32 (cat of cand/hist/obj visual rows; may require grad)
+    outputs: mode 'rows' -> final-RMSNorm'ed hidden states at ``rows`` ([R, D] bf16)
+             mode 'loss' -> mean shifted-CE loss over ``pp.loss_rows`` (fp32 scalar)
+    backward accumulates all LM weight gradients in place and returns d vis.
+    """
+
+    @staticmethod
+    def forward(ctx, lm: "ModifiedLlamaForCausalLM", pp: PackedPrompt, vis: Optional[torch.Tensor], mode: str,
+                rows: Optional[torch.Tensor], anchor):
+        core, d = lm.core, lm.dims
+        train = torch.is_grad_enabled() and lm.training_enabled
+        E = lm.model.embed_tokens.weight.data
+        x = ops.embed_fwd(pp.ids, E, pp.vis_src if vis is not None else None, vis)
+        hid = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=train)
+        ctx.lm, ctx.pp, ctx.mode, ctx.has_vis = lm, pp, mode, vis is not None
+        ctx.n_vis = 0 if vis is None else vis.shape[0]
+        if mode == "rows":
+            g = ops.gather_rows(hid, rows)
+            hn, rstd = ops.rmsnorm_fwd(g, lm.model.norm.weight.data, d.rms_eps)
+            ctx.saved = (g, rstd, rows, hid.shape)
+            return hn
+        # ---- LM loss on the label rows only ----
+        rows = pp.loss_rows
+        g = ops.gather_rows(hid, rows)
+        hn, rstd = ops.rmsnorm_fwd(g, lm.model.norm.weight.data, d.rms_eps)
+        V = lm.lm_head.weight.shape[0]
+        logits = torch.empty((g.shape[0], (V + 63) // 64 * 64), dtype=bf16, device=g.device)[:, :V]   # 16-byte aligned rows
+        ops.gemm(hn, lm.lm_head.weight.data, out=logits)                 # [Nl, V] bf16
+        row_loss, dlogits = ops.ce_fwd_bwd(logits, pp.loss_tgt, lm.special_ids_dev,
+                                           grad_scale=(1.0 / max(pp.n_loss, 1)) if train else None)
+        loss = row_loss.sum() / max(pp.n_loss, 1)
+        ctx.saved = (g, rstd, rows, hid.shape, hn, dlogits)
+        return loss.to(bf16) if lm.model_type == bf16 else loss           # reference: CE on bf16 logits -> bf16 loss
+
+    @staticmethod
+    def backward(ctx, dout):
+        lm, pp = ctx.lm, ctx.pp
+        core, d = lm.core, lm.dims
+        normw = lm.model.norm.weight
+        if ctx.mode == "rows":
+            g, rstd, rows, shape = ctx.saved
+            dy = dout.contiguous().to(bf16)
+        else:
+            g, rstd, rows, shape, hn, dlogits = ctx.saved
+            # dlogits was produced with scale 1/N; fold the incoming scalar gradient in on the device (no sync)
+            dlogits = (dlogits.float() * dout.float()).to(bf16)
+            dy = ops.gemm(dlogits, lm.lm_head.weight.data, b_mn=True)                    # [Nl, D]
+            ops.gemm(dlogits, hn, a_mn=True, b_mn=True, out=lm.lm_head.weight.grad, addend=lm.lm_head.weight.grad)
+        dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)
+        dhid = torch.zeros(shape, dtype=bf16, device=dg.device)
+        ops.scatter_rows_(dg, rows, dhid)
+        dx = core.backward(dhid)
+        ops.embed_bwd_weight_(dx, pp.ids, lm.model.embed_tokens.weight.grad)
+        dvis = ops.embed_bwd_vis(dx, pp.vis_src, ctx.n_vis) if ctx.has_vis else None
+        ctx.saved = None
+        return None, None, dvis, None, None, None
+
+
+class ModifiedLlamaForCausalLM(nn.Module):
+    def __init__(self, config, extra_config=None, tokenizer=None):
+        """config: object with hidden_size, intermediate_size, num_hidden_layers, num_attention_heads, vocab_size,
+        rms_norm_eps (a transformers LlamaConfig works).  extra_config.precision as in the reference."""
+        super().__init__()
+        precision = getattr(extra_config, "precision", "amp_bf16") if extra_config is not None else "amp_bf16"
+        if not ("bf16" in precision or "bfloat16" in precision):
+            raise NotImplementedError(f"navillm_b200 computes the LM in bf16 (reference 'amp_bf16'); got precision={precision!r}")
+        self.model_type = bf16
+        self.config = config
+        self.hidden_size = config.hidden_size
+        self.dims = LlamaDims(hidden=config.hidden_size, n_layers=config.num_hidden_layers, n_heads=config.num_attention_heads,
+                              inter=config.intermediate_size, vocab=config.vocab_size,
+                              rms_eps=getattr(config, "rms_norm_eps", 1e-6), rope_theta=getattr(config, "rope_theta", 10000.0))
+        if self.dims.head_dim != 128:
+            raise NotImplementedError("attention kernels are built for head_dim = 128 (Vicuna-7B)")
+        self.model = LlamaModelParams(self.dims)
+        self.lm_head = _Linear(self.dims.vocab, self.dims.hidden)
+        self.core: Optional[LlamaCore] = None
+        self.training_enabled = True
+        self.register_buffer("_anchor", torch.zeros((), dtype=torch.float32), persistent=False)
+        if tokenizer is not None:
+            self._set_tokenizer(tokenizer)
+
+    # ---- tokenizer front-end (models/modified_lm.py:56-87) ----
+    def init_tokenizer(self, pretrained_model_name_or_path: Optional[str]):
+        try:
+            tok = HFTokenizerAdapter(pretrained_model_name_or_path)
+        except Exception:
+            tok = SyntheticTokenizer(base_vocab=self.dims.vocab if self.dims.vocab < 32000 else 32000)
+        self._set_tokenizer(tok)
+
+    def _set_tokenizer(self, tok):
+        self.tokenizer = tok
+        self.cand_token, self.hist_token, self.obj_token = ["<cand>"], ["<hist>"], ["<obj>"]
+        self.cls_token = ["<cls_1>", "<cls_2>"]
+        self.cand_token_id = [tok.special["<cand>"]]
+        self.hist_token_id = [tok.special["<hist>"]]
+        self.obj_token_id = [tok.special["<obj>"]]
+        self.cls_token_id = [tok.special["<cls_1>"], tok.special["<cls_2>"]]
+        self.special_token_ids = self.cand_token_id + self.hist_token_id + self.obj_token_id + self.cls_token_id
+        self.resize_token_embeddings(len(tok))
+
+    def resize_token_embeddings(self, n: int):
+        old = self.model.embed_tokens.weight
+        if old.shape[0] == n:
+            return
+        assert self.core is None, "resize_token_embeddings after materialisation"
+        D = old.shape[1]
+        for holder in (self.model.embed_tokens, self.lm_head):
+            w = holder.weight.data
+            new = torch.empty(n, D, dtype=w.dtype)
+            k = min(n, w.shape[0])
+            new[:k] = w[:k]
+            if n > k:
+                new[k:] = (torch.randn(n - k, D) * 0.02).to(w.dtype)
+            holder.weight = nn.Parameter(new)
+        self.dims.vocab = n
+        self.config.vocab_size = n
+
+    def tokenize(self, text, add_special_tokens: bool = True):
+        return self.tokenizer(text, max_length=1024, padding=True, truncation=True, return_tensors="pt",
+                              add_special_tokens=add_special_tokens, return_token_type_ids=True)
+
+    # ---- device materialisation ----
+    def lm_parameters(self) -> List[nn.Parameter]:
+        ps: List[nn.Parameter] = []
+        for lyr in self.model.layers:
+            a, m = lyr.self_attn, lyr.mlp
+            ps += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.o_proj.weight, m.gate_proj.weight, m.up_proj.weight,
+                   m.down_proj.weight, lyr.input_layernorm.weight, lyr.post_attention_layernorm.weight]
+        ps += [self.model.embed_tokens.weight, self.model.norm.weight, self.lm_head.weight]
+        return ps
+
+    def materialize(self, device: torch.device, extra_params: Optional[List[nn.Parameter]] = None) -> FlatParams:
+        """Move the LM parameters into one flat bf16 buffer on ``device`` (+ ``extra_params``: the bf16 heads of
+        NavModel) and build the fused-view driver.  Idempotent while the views are intact."""
+        if self.core is not None and self.flat.intact():
+            return self.flat
+        if extra_params is not None:
+            self._extra_params = list(extra_params)
+        params = self.lm_parameters() + list(getattr(self, "_extra_params", []))
+        self.flat = FlatParams(params, device)
+        self.core = LlamaCore(self.dims, self.model, self.flat)
+        self.special_ids_dev = torch.tensor(self.special_token_ids, dtype=torch.int32, device=device)
+        return self.flat
+
+    def _device(self) -> torch.device:
+        return self.model.norm.weight.device
+
+    def _ensure(self):
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("navillm_b200 has no CPU path: move the model to a CUDA device first")
+        if self.core is None:
+            self.materialize(dev)
+            return
+        p0 = self.flat.params[0]
+        if p0.data_ptr() != self.flat._ptr0:              # parameters were moved/replaced (.to(), load): re-home
+            self.core = None
+            self.materialize(dev)
+        elif p0.grad is None or p0.grad.data_ptr() != self.flat.flat_grad.data_ptr():
+            self.flat.reattach_grads()                    # optimizer.zero_grad(set_to_none=True)
+
+    # ---- packed entry points used by NavModel ----
+    def hidden_rows(self, pp: PackedPrompt, vis: Optional[torch.Tensor], rows: torch.Tensor) -> torch.Tensor:
+        self._ensure()
+        anchor = self._anchor.detach().requires_grad_(torch.is_grad_enabled())
+        return _LMFn.apply(self, pp, vis, "rows", rows, anchor)
+
+    def lm_loss(self, pp: PackedPrompt, vis: Optional[torch.Tensor]) -> torch.Tensor:
+        self._ensure()
+        anchor = self._anchor.detach().requires_grad_(torch.is_grad_enabled())
+        return _LMFn.apply(self, pp, vis, "loss", None, anchor)
+
+    @staticmethod
+    def cat_vis(cand_vis, hist_vis, obj_vis, pp: PackedPrompt) -> Optional[torch.Tensor]:
+        parts = []
+        for name, v, n in (("cand", cand_vis, pp.n_cand), ("hist", hist_vis, pp.n_hist), ("obj", obj_vis, pp.n_obj)):
+            if n == 0:
+                continue
+            if v is None or v.shape[0] != n:
+                raise RuntimeError(f"{n} <{name}> tokens in the prompts but {0 if v is None else v.shape[0]} {name}_vis rows "
+                                   f"(models/modified_lm.py:105-110 requires equal counts)")
+            parts.append(v.to(torch.float32))
+        if not parts:
+            return None
+        return parts[0].contiguous() if len(parts) == 1 else torch.cat(parts, dim=0)
+
+    # ---- reference-compatible forward (models/modified_lm.py:89-146) ----
+    def forward(self, input_ids, attention_mask, labels=None, cand_vis=None, hist_vis=None, obj_vis=None,
+                return_logits: bool = False, **kwargs):
+        self._ensure()
+        dev = self._device()
+        pp = PackedPrompt(input_ids, attention_mask, self, dev, labels=labels)
+        vis = self.cat_vis(cand_vis, hist_vis, obj_vis, pp)
+        loss = self.lm_loss(pp, vis) if labels is not None else None
+        hidden = logits = None
+        if labels is None or return_logits:
+            all_rows = torch.arange(pp.T, device=dev, dtype=torch.int32)
+            hn = self.hidden_rows(pp, vis, all_rows)
+            flat = torch.from_numpy(pp.flat_rows).to(dev)
+            hidden = torch.zeros((pp.B * pp.S, self.dims.hidden), dtype=bf16, device=dev).index_copy(0, flat, hn)
+            hidden = hidden.view(pp.B, pp.S, -1)
+            if return_logits:
+                lg = ops.gemm(hn.detach().contiguous(), self.lm_head.weight.data)
+                lg[:, self.special_token_ids] = float("-inf")
+                logits = torch.zeros((pp.B * pp.S, lg.shape[1]), dtype=bf16, device=dev).index_copy(0, flat, lg).view(pp.B, pp.S, -1)
+        return LMOutput(loss=loss, logits=logits, past_key_values=None, hidden_states=hidden, attentions=None)

@@ -223,7 +223,8 @@ def ce_fwd_bwd(logits, labels, special_ids, *, grad_scale=None):
     """Per-row masked CE on bf16 logits; returns (row_loss fp32 [N], dlogits bf16 [N,V] or None)."""
     N, V = logits.shape
     row_loss = torch.empty((N,), dtype=torch.float32, device=logits.device)
-    dlogits = torch.empty((N, V), dtype=bf16, device=logits.device) if grad_scale is not None else None
+    # rows padded to a multiple of 64 elements so dlogits can feed the tcgen05 GEMMs (16-byte aligned rows)
+    dlogits = torch.empty((N, (V + 63) // 64 * 64), dtype=bf16, device=logits.device)[:, :V] if grad_scale is not None else None
     check(_lib.load().nv_ce_fwd_bwd(ptr(logits), i64(logits.stride(0)), ptr(labels), ptr(special_ids),
                                     i32(special_ids.numel()), ptr(row_loss), ptr(dlogits),
                                     i64(dlogits.stride(0) if dlogits is not None else 0), i32(N), i32(V),
@@ -364,3 +365,18 @@ def rows_scatter_add_(dst, idx, src, alpha=1.0):
     check(_lib.load().nv_rows_scatter_add(ptr(dst), i64(dst.stride(0)), ptr(idx), ptr(src), i64(src.stride(0)), f32(alpha),
                                           i32(src.shape[0]), i32(src.shape[1]), stream_ptr()), "nv_rows_scatter_add")
     return dst
+
+
+def logit_scatter_fwd(pred, slot, B, G):
+    out = torch.empty((B, G), dtype=bf16, device=pred.device)
+    check(_lib.load().nv_logit_scatter_fwd(ptr(pred), i32(pred.shape[1]), ptr(slot), ptr(out), i32(B), i32(G), stream_ptr()),
+          "nv_logit_scatter_fwd")
+    return out
+
+
+def logit_scatter_bwd(dout, slot, O):
+    B, G = dout.shape
+    dpred = torch.zeros((B, O), dtype=bf16, device=dout.device)
+    check(_lib.load().nv_logit_scatter_bwd(ptr(dout), ptr(slot), ptr(dpred), i32(O), i32(B), i32(G), stream_ptr()),
+          "nv_logit_scatter_bwd")
+    return dpred
