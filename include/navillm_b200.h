@@ -1,0 +1,117 @@
+/* navillm_b200 — C ABI of the B200-native NaviLLM hot path (libnavillm_b200.so, sm_100a only).
+ *
+ * The reference (zd11024/NaviLLM) is pure Python/PyTorch and has NO native interface of its own: its
+ * "operator API" for this path is the set of torch calls made inside NavModel.forward() and below
+ * (SURVEY.md §8b).  Every entry point here replaces a group of those calls; the reference call site each
+ * one stands in for is cited as file:line relative to the reference repository root.
+ *
+ * Conventions
+ *   - raw DEVICE pointers (never host pointers, never torch types), explicit sizes and leading dimensions
+ *     in ELEMENTS, `stream` = a cudaStream_t passed as void*;
+ *   - the library allocates nothing on the device: outputs and workspaces are caller-owned;
+ *   - return value: 0 = ok; negative = argument / environment error (NV_ERR_*); positive = cudaError_t.
+ *     nv_last_error() returns a thread-local message for the last failure;
+ *   - there is NO CPU fallback: without an sm_100 device every compute entry fails (NV_ERR_NO_DEVICE or a
+ *     CUDA error), it never computes on the host;
+ *   - bf16 tensors are row-major with 16-byte aligned rows (leading dimensions multiples of 8 elements).
+ */
+#ifndef NAVILLM_B200_H_
+#define NAVILLM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NV_OK 0
+#define NV_ERR_BAD_ARG (-1)
+#define NV_ERR_NO_DEVICE (-2)
+#define NV_ERR_UNSUPPORTED (-3)
+
+#define NV_GEMM_ADD 1u     /* C = bf16(bf16(acc) + addend): residual add / in-place gradient accumulation */
+#define NV_GEMM_OUT_F32 2u /* C is fp32 */
+
+/* ---- runtime ---------------------------------------------------------------------------------------- */
+const char* nv_last_error(void);
+int nv_abi_version(void);
+int nv_device_check(void); /* NV_OK iff the current device is sm_100-class */
+int nv_sm_count(void);
+
+/* ---- tcgen05 bf16 GEMM (csrc/gemm_bf16.cu) -----------------------------------------------------------
+ * C[M,N] = A·B (+addend).  a_mn=0: A is [M,K]; a_mn=1: A is [K,M].  b_mn=0: B is [N,K] (nn.Linear weight);
+ * b_mn=1: B is [K,N].  Replaces every nn.Linear of the LLaMA block and lm_head and their autograd dgrad /
+ * wgrad: models/modified_lm.py:112-116 (HF LlamaDecoderLayer q/k/v/o/gate/up/down_proj) and :120 (lm_head).
+ * block_n: 0 (auto), 128 or 256. */
+int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* C, int64_t ldc,
+                 const void* addend, int64_t ld_add, int M, int N, int K, unsigned flags, int block_n, void* stream);
+
+/* ---- flash attention on packed rows (csrc/attn_fwd.cu, attn_bwd.cu) ------------------------------------
+ * Causal self-attention of HF LlamaAttention (eager softmax(QK^T/sqrt(d)+mask)V; call site
+ * models/modified_lm.py:112-116) and its backward (loss.backward(): tasks/agents/mp3d_agent.py:750-757).
+ * q,k,v,o,dout,dq,dk,dv: bf16 [T, H*128] column views; lse: fp32 [H,T]; cu_seqlens: int32 [B+1];
+ * total_qblocks = sum_b ceil(len_b/128); dvec: fp32 workspace [H*T]. */
+int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
+                float* lse, const int* cu_seqlens, int B, int T, int H, int head_dim, int total_qblocks, float scale,
+                void* stream);
+int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
+                int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* dvec, void* dq, int64_t lddq,
+                void* dk, int64_t lddk, void* dv, int64_t lddv, const int* cu_seqlens, int B, int T, int H, int head_dim,
+                int total_blocks, float scale, void* stream);
+
+/* ---- row-wise LM kernels (csrc/lm_ops.cu) ---------------------------------------------------------------
+ * LlamaRMSNorm, rotate-half RoPE, SwiGLU (HF LLaMA via models/modified_lm.py:112-116); embedding gather +
+ * visual-token scatter-add (models/modified_lm.py:100-110); <cls_1> head (models/nav_model.py:237,445);
+ * action-logit scatter (models/nav_model.py:239-242, :446-447); masked token CE (models/modified_lm.py:122-137). */
+int nv_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t ldy, float* rstd, int T, int D, float eps,
+                   void* stream);
+int nv_rmsnorm_bwd_partials(void);
+int nv_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const float* rstd, const void* dy, int64_t lddy,
+                   const void* dres, int64_t lddres, void* dx, int64_t lddx, void* dw, int accumulate_dw, float* workspace,
+                   int T, int D, void* stream);
+int nv_rope_inplace(void* qkv, int64_t ld, const int* pos, const void* cos_t, const void* sin_t, int T, int n_heads,
+                    int head_dim, int backward, void* stream);
+int nv_swiglu_fwd(const void* gu, int64_t ldgu, void* h, int64_t ldh, int T, int F, void* stream);
+int nv_swiglu_bwd(const void* gu, int64_t ldgu, const void* dh, int64_t lddh, void* dgu, int64_t lddgu, int T, int F,
+                  void* stream);
+int nv_embed_fwd(const int* ids, const void* E, int V, const int* vis_src, const float* vis, void* out, int T, int D,
+                 void* stream);
+int nv_embed_bwd_vis(const void* dx, const int* vis_src, float* dvis, int T, int D, void* stream);
+int nv_embed_bwd_weight(const void* dx, const int* order, const int* sorted_ids, void* dE, int T, int D, void* stream);
+int nv_gather_rows(const void* src, int64_t lds, const int* rows, void* dst, int64_t ldd, int R, int D, void* stream);
+int nv_scatter_rows(const void* src, int64_t lds, const int* rows, void* dst, int64_t ldd, int R, int D, void* stream);
+int nv_head_fwd(const void* x, int64_t ldx, const void* W, const void* bias, void* out, int R, int O, int D, void* stream);
+int nv_head_bwd(const void* dy, const void* x, int64_t ldx, const void* W, void* dx, int64_t lddx, void* dW, void* db, int R,
+                int O, int D, void* stream);
+int nv_logit_scatter_fwd(const void* pred, int O, const int* slot, void* out, int B, int G, void* stream);
+int nv_logit_scatter_bwd(const void* dout, const int* slot, void* dpred, int O, int B, int G, void* stream);
+int nv_ce_fwd_bwd(const void* logits, int64_t ld, const int* labels, const int* special, int n_special, float* row_loss,
+                  void* dlogits, int64_t ldd, int N, int V, float grad_scale, void* stream);
+
+/* ---- fp32 panorama encoder / fusion kernels (csrc/pano_ops.cu) --------------------------------------------
+ * nn.Linear / LayerNorm / GELU / nn.MultiheadAttention(key_padding_mask) of ImageEmbeddings and the DETR
+ * pre-LN encoder (models/image_embedding.py:51-121, models/detr_transformer.py:170-182), and the gather /
+ * scatter glue of NavModel.forward_navigation (models/nav_model.py:146-224), forward and backward. */
+int nv_sgemm(const float* A, int64_t lda, int ta, const float* B, int64_t ldb, int tb, float* C, int64_t ldc,
+             const float* bias, int M, int N, int K, int accumulate, void* stream);
+int nv_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, const float* addend, int64_t ldadd,
+                     float* y, int64_t ldy, float* mean, float* rstd, int R, int D, float eps, void* stream);
+int nv_layernorm_bwd_partials(void);
+int nv_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, const float* mean, const float* rstd, const float* dy,
+                     int64_t lddy, float* dx, int64_t lddx, int accumulate_dx, float* dgamma, float* dbeta, float* workspace,
+                     int R, int D, void* stream);
+int nv_colsum_f32(const float* src, int64_t ld, int R, int D, float* dst, int accumulate, void* stream);
+int nv_gelu_fwd(const float* z, float* a, int64_t n, void* stream);
+int nv_gelu_bwd(const float* z, const float* da, float* dz, int64_t n, void* stream);
+int nv_mha_fwd(const float* qkv, const int* lens, float* out, float* P, int B, int N, int H, int hd, void* stream);
+int nv_mha_bwd(const float* qkv, const float* dout, const float* P, float* dS, float* dqkv, const int* lens, int B, int N,
+               int H, int hd, void* stream);
+int nv_rows_combine(float* out, int64_t ldo, const float* A, int64_t lda, const int* ia, float alpha, const float* Bm,
+                    int64_t ldb, const int* ib, float beta, int R, int D, int accumulate, void* stream);
+int nv_rows_scatter_add(float* dst, int64_t ldd, const int* idx, const float* src, int64_t lds, float alpha, int R, int D,
+                        void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NAVILLM_B200_H_ */

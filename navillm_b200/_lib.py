@@ -41,7 +41,15 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     return _lib
 
 
+launch_count = 0          # kernels launched through the C ABI since import (bench.py reports the per-step delta)
+
+# entry points that launch more than one kernel per call
+_MULTI = {"nv_rmsnorm_bwd": 2, "nv_attn_bwd": 3, "nv_layernorm_bwd": 3, "nv_head_bwd": 2, "nv_mha_bwd": 2}
+
+
 def check(status: int, what: str) -> None:
+    global launch_count
+    launch_count += _MULTI.get(what, 1)
     if status != 0:
         msg = load().nv_last_error().decode(errors="replace")
         raise NvError(f"{what} failed with status {status}: {msg}")

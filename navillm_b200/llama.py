@@ -203,17 +203,16 @@ class LlamaCore:
             self.wd.append(m.down_proj.weight.data)
             self.gd.append(m.down_proj.weight.grad)
         self.cos, self.sin = rope_tables(dims, flat.flat.device)
-        self.saved: List[_Saved] = []
-        self.meta = None
 
     # -------------------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True) -> torch.Tensor:
+    def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True):
         """x: [T, D] bf16 input embeddings (packed); pos: int32 [T]; cu: int32 [B+1] (device); seqlens: host
-        lengths.  Returns the residual stream after the last layer, BEFORE the final RMSNorm."""
+        lengths.  Returns (residual stream after the last layer BEFORE the final RMSNorm, tape) where ``tape``
+        holds the per-layer activations for ``backward`` (None when save=False).  The tape travels with the
+        caller (autograd ctx), so several forwards may be in flight before their backwards run."""
         d = self.d
         H = d.n_heads
-        self.saved = []
-        self.meta = (pos, cu, list(seqlens))
+        saved: List[_Saved] = []
         for l, lyr in enumerate(self.model.layers):
             s = _Saved()
             s.x = x
@@ -227,19 +226,20 @@ class LlamaCore:
             s.h = ops.swiglu_fwd(s.gu)
             x = ops.gemm(s.h, self.wd[l], addend=s.xm)
             if save:
-                self.saved.append(s)
-        return x
+                saved.append(s)
+        return x, ((saved, (pos, cu, list(seqlens))) if save else None)
 
     # -------------------------------------------------------------------------------------------------
-    def backward(self, dx: torch.Tensor) -> torch.Tensor:
-        """dx: [T, D] bf16 gradient w.r.t. the forward's return value.  Accumulates every weight gradient
-        in place and returns the gradient w.r.t. the input embeddings."""
-        assert self.saved, "LlamaCore.backward without a saved forward"
+    def backward(self, dx: torch.Tensor, tape) -> torch.Tensor:
+        """dx: [T, D] bf16 gradient w.r.t. the forward's hidden output; ``tape`` from that forward (consumed).
+        Accumulates every weight gradient in place and returns the gradient w.r.t. the input embeddings."""
+        if tape is None:
+            raise RuntimeError("LlamaCore.backward: the forward ran without saving activations (no_grad / eval-only)")
+        saved, (pos, cu, seqlens) = tape
         d = self.d
         H = d.n_heads
-        pos, cu, seqlens = self.meta
         for l in range(d.n_layers - 1, -1, -1):
-            lyr, s = self.model.layers[l], self.saved[l]
+            lyr, s = self.model.layers[l], saved[l]
             # ---- MLP:  x_out = xm + down(swiglu(gate_up(rmsnorm2(xm)))) ----
             dh = ops.gemm(dx, self.wd[l], b_mn=True)                                   # [T,F]  dgrad
             ops.gemm(dx, s.h, a_mn=True, b_mn=True, out=self.gd[l], addend=self.gd[l])  # dWd += dx^T h
@@ -263,6 +263,5 @@ class LlamaCore:
             dx = ops.rmsnorm_bwd(s.x, lyr.input_layernorm.weight.data, s.rstd1, dxn, dres=dxm,
                                  dw=lyr.input_layernorm.weight.grad)
             del dxn, dxm
-            self.saved[l] = None
-        self.saved = []
+            saved[l] = None
         return dx

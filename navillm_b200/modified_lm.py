@@ -103,12 +103,12 @@ class _LMFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lm: "ModifiedLlamaForCausalLM", pp: PackedPrompt, vis: Optional[torch.Tensor], mode: str,
-                rows: Optional[torch.Tensor], anchor):
+                rows: Optional[torch.Tensor], train: bool, anchor):
+        # NB: grad mode is always off inside Function.forward, so `train` is decided by the caller
         core, d = lm.core, lm.dims
-        train = torch.is_grad_enabled() and lm.training_enabled
         E = lm.model.embed_tokens.weight.data
         x = ops.embed_fwd(pp.ids, E, pp.vis_src if vis is not None else None, vis)
-        hid = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=train)
+        hid, ctx.tape = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=train)
         ctx.lm, ctx.pp, ctx.mode, ctx.has_vis = lm, pp, mode, vis is not None
         ctx.n_vis = 0 if vis is None else vis.shape[0]
         if mode == "rows":
@@ -146,11 +146,11 @@ class _LMFn(torch.autograd.Function):
         dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)
         dhid = torch.zeros(shape, dtype=bf16, device=dg.device)
         ops.scatter_rows_(dg, rows, dhid)
-        dx = core.backward(dhid)
+        dx = core.backward(dhid, ctx.tape)
         ops.embed_bwd_weight_(dx, pp.ids, lm.model.embed_tokens.weight.grad)
         dvis = ops.embed_bwd_vis(dx, pp.vis_src, ctx.n_vis) if ctx.has_vis else None
-        ctx.saved = None
-        return None, None, dvis, None, None, None
+        ctx.saved = ctx.tape = None
+        return None, None, dvis, None, None, None, None
 
 
 class ModifiedLlamaForCausalLM(nn.Module):
@@ -260,13 +260,15 @@ class ModifiedLlamaForCausalLM(nn.Module):
     # ---- packed entry points used by NavModel ----
     def hidden_rows(self, pp: PackedPrompt, vis: Optional[torch.Tensor], rows: torch.Tensor) -> torch.Tensor:
         self._ensure()
-        anchor = self._anchor.detach().requires_grad_(torch.is_grad_enabled())
-        return _LMFn.apply(self, pp, vis, "rows", rows, anchor)
+        train = torch.is_grad_enabled() and self.training_enabled
+        anchor = self._anchor.detach().requires_grad_(train)
+        return _LMFn.apply(self, pp, vis, "rows", rows, train, anchor)
 
     def lm_loss(self, pp: PackedPrompt, vis: Optional[torch.Tensor]) -> torch.Tensor:
         self._ensure()
-        anchor = self._anchor.detach().requires_grad_(torch.is_grad_enabled())
-        return _LMFn.apply(self, pp, vis, "loss", None, anchor)
+        train = torch.is_grad_enabled() and self.training_enabled
+        anchor = self._anchor.detach().requires_grad_(train)
+        return _LMFn.apply(self, pp, vis, "loss", None, train, anchor)
 
     @staticmethod
     def cat_vis(cand_vis, hist_vis, obj_vis, pp: PackedPrompt) -> Optional[torch.Tensor]:

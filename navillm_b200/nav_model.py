@@ -358,7 +358,9 @@ class NavModel(nn.Module):
         cand_embeds = _RowsFn.apply(fuse, self._idx(sel), None, None, len(sel))
         hist_vis_input = self._flatten_hist(batch["hist_vis"], dev)
 
-        text = self.lang_model.tokenize(batch["prompts"])
+        # `text_input` (optional, not in the reference): an already tokenised TokenBatch for callers that keep
+        # the prompt ids resident; otherwise tokenise on the host exactly like models/nav_model.py:211
+        text = batch["text_input"] if batch["text_input"] is not None else self.lang_model.tokenize(batch["prompts"])
         pp = PackedPrompt(text["input_ids"], text["attention_mask"], self.lang_model, dev)
         vis = self.lang_model.cat_vis(cand_embeds, hist_vis_input, None, pp)
         if pp.n_cls != B:

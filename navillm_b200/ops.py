@@ -12,6 +12,8 @@ from ._lib import check, f32, i32, i64, ptr, stream_ptr, u32
 
 bf16 = torch.bfloat16
 
+gemm_timer = None   # set to a list by bench.py to collect (start_event, end_event, flops) per GEMM launch
+
 
 def _rowmajor(t: torch.Tensor, name: str) -> None:
     if t.dim() != 2 or t.stride(1) != 1:
@@ -44,9 +46,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if out_f32:
         flags |= _lib.GEMM_OUT_F32
     lib = _lib.load()
+    timer = gemm_timer
+    if timer is not None:       # bench.py: CUDA events on the launching stream around every GEMM launch
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
     check(lib.nv_gemm_bf16(ptr(a), i64(a.stride(0)), i32(a_mn), ptr(b), i64(b.stride(0)), i32(b_mn), ptr(out),
                            i64(out.stride(0)), ptr(addend), i64(addend.stride(0) if addend is not None else 0),
                            i32(M), i32(N), i32(K), u32(flags), i32(block_n), stream_ptr()), "nv_gemm_bf16")
+    if timer is not None:
+        en.record()
+        timer.append((st, en, 2.0 * M * N * K))
     return out
 
 

@@ -71,11 +71,11 @@ def test_llama_stack_forward_backward(cuda_dev):
 
     rows, pos, cu, seqlens = pack(emb, mask)
     x = emb.view(B * S, D)[rows].to(cuda_dev).contiguous()
-    hid = core.forward(x, pos.to(cuda_dev), cu.to(cuda_dev), seqlens)
+    hid, tape = core.forward(x, pos.to(cuda_dev), cu.to(cuda_dev), seqlens)
     hn, rstd = ops.rmsnorm_fwd(hid, model.norm.weight.data, dims.rms_eps)
     dy = G.view(B * S, D)[rows].to(cuda_dev).contiguous()
     dhid = ops.rmsnorm_bwd(hid, model.norm.weight.data, rstd, dy, dw=model.norm.weight.grad)
-    dx = core.backward(dhid)
+    dx = core.backward(dhid, tape)
     torch.cuda.synchronize()
 
     def check(name, mine, truth, ref):
