@@ -1,0 +1,375 @@
+"""bench.py — nav-steps/sec of the NaviLLM per-step hot path (panorama + navigation forward, action CE,
+backward) on synthetic R2R-shaped batches, Vicuna-7B, bf16, on N B200s (one process per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]                 # this repo (sm_100a kernels)
+    python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]   # the reference path on host cores
+
+Workload = BASELINE.json configs[1] ("R2R-shaped training step: batch=16, 36 views, hist=8, seq<=1024,
+Vicuna-7B bf16, 1xB200"; SURVEY.md §8d "C2"): B=16 prompts with lengths U{256..1024} (left-padded by the
+tokenizer, never computed here because rows are packed), 36 views x 1408-d, 8 history tokens, 24 graph nodes,
+15 candidates + stop.  One bench "step" = one batch of 16 navigation steps:
+    model('panorama') -> model('navigation') -> CE(fuse_logits, targets) -> backward.
+`value` times that with all inputs resident in HBM; `e2e` times the same call sequence through the public
+API from HOST (pinned) buffers: per step the H2D copy of every input tensor, host tokenisation and index
+building, and a D2H read of the loss.  Multi-GPU: weak scaling, one batch per rank, ONE NCCL all-reduce of the
+flat gradient buffers per step inside the timed region.
+
+The `--impl reference` arm (and `cpu_baseline`) time the CPU oracle port of the reference algorithm
+(oracle/navillm_oracle.py; kind "port": the reference is Python and cannot travel to the GPU box) on the
+host cores over a bounded sample: full-width Vicuna-7B layers, B=1, one prompt of the workload's mean
+length, `--cpu-layers` of the 32 layers timed fwd+bwd and scaled to 32.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import types
+from pathlib import Path
+
+import numpy as np
+import torch
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+D_MODEL, N_LAYERS, N_HEADS, D_FF, VOCAB = 4096, 32, 32, 11008, 32000
+IMG_FEAT = 1408
+B_STEP, N_VIEWS, N_HIST, N_GMAP, N_CAND = 16, 36, 8, 24, 16
+LEN_LO, LEN_HI = 256, 1024
+
+
+def peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return {"bf16_tflops": j.get("bf16_tflops_sustained", j.get("bf16_tflops")), "hbm_gbs": j.get("hbm_gbs"), "src": "measured"}
+    return {"bf16_tflops": 1400.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# synthetic workload
+# ---------------------------------------------------------------------------------------------------------
+def make_workload(seed: int, B: int = B_STEP):
+    rng = np.random.RandomState(seed)
+    g = torch.Generator().manual_seed(seed)
+    lens = rng.randint(LEN_LO, LEN_HI + 1, size=B)
+    words = [f"w{i}" for i in range(5000)]
+    prompts = []
+    n_c = N_CAND - 1
+    for b in range(B):
+        n_words = int(lens[b]) - (1 + N_HIST + n_c + 1 + 4)          # bos + hist + cand + cls + 4 section words
+        instr = " ".join(words[i] for i in rng.randint(0, len(words), size=max(n_words, 1)))
+        prompts.append("Instruction " + instr + " History " + " ".join(["<hist>"] * N_HIST) + " Candidates stop "
+                       + " ".join(["<cand>"] * n_c) + " Answer <cls_1>")
+    heading = torch.rand(B, N_VIEWS, generator=g) * 6.2831853
+    elev = (torch.randint(0, 3, (B, N_VIEWS), generator=g).float() - 1) * 0.5235988
+    loc = torch.stack([heading.sin(), heading.cos(), elev.sin(), elev.cos()], -1)
+    loc = torch.cat([loc, torch.ones(B, N_VIEWS, 3)], -1)
+    nav_types = torch.zeros(B, N_VIEWS, dtype=torch.long)
+    nav_types[:, :n_c] = 1
+    # graph: slot 0 = stop, N_HIST visited nodes, then unvisited; the first n_c unvisited are the current candidates
+    gmap_vpids = [[None] + [f"v{j}" for j in range(N_HIST)] + [f"c{j}" for j in range(N_GMAP - 1 - N_HIST)] for _ in range(B)]
+    visited = torch.zeros(B, N_GMAP, dtype=torch.bool)
+    visited[:, 1:1 + N_HIST] = True
+    step_ids = torch.zeros(B, N_GMAP, dtype=torch.long)
+    step_ids[:, 1:1 + N_HIST] = torch.arange(1, N_HIST + 1)
+    host = {
+        "view_img_fts": torch.randn(B, N_VIEWS, IMG_FEAT, generator=g),
+        "loc_fts": loc,
+        "nav_types": nav_types,
+        "vp_pos_fts": torch.randn(B, N_VIEWS + 1, 14, generator=g),
+        "gmap_img_embeds": torch.randn(B, N_GMAP, D_MODEL, generator=g),
+        "gmap_pos_fts": torch.randn(B, N_GMAP, 7, generator=g),
+        "hist_vis": torch.randn(B, N_HIST, D_MODEL, generator=g),
+    }
+    meta = {
+        "view_lens": torch.full((B,), N_VIEWS, dtype=torch.long),
+        "gmap_step_ids": step_ids, "gmap_masks": torch.ones(B, N_GMAP, dtype=torch.bool), "gmap_visited_masks": visited,
+        "gmap_vpids": gmap_vpids, "vp_cand_vpids": [[None] + [f"c{j}" for j in range(n_c)] for _ in range(B)],
+        "prompts": prompts, "targets": torch.from_numpy(rng.randint(0, N_CAND, size=B)).long(),
+        "lens": lens,
+    }
+    # candidate slot -> gmap column of the target (slot 0 = stop = column 0; candidate j = column 1+N_HIST+j)
+    tgt_cols = torch.where(meta["targets"] == 0, torch.zeros_like(meta["targets"]), meta["targets"] + N_HIST)
+    meta["target_cols"] = tgt_cols
+    return host, meta
+
+
+def build_model(dev, seed=0):
+    from navillm_b200.nav_model import NavModel
+    from navillm_b200.tokenizer import SyntheticTokenizer
+    args = types.SimpleNamespace(precision="amp_bf16", pretrained_model_name_or_path="vicuna-7b-synthetic", image_feat_size=IMG_FEAT,
+                                 angle_feat_size=4, obj_feat_size=768, enable_og=True, fuse_obj=False, feat_dropout=0.4,
+                                 resume_from_checkpoint=None, from_scratch=True, device=str(dev), seed=seed)
+    mc = types.SimpleNamespace(num_pano_layers=2, tokenizer=SyntheticTokenizer(base_vocab=VOCAB))
+    torch.manual_seed(seed)
+    model = NavModel(args, None, mc)
+    model.train()
+    return model
+
+
+def nav_step(model, dev_in, meta, dev, text=None):
+    """One batch of navigation steps through the public API; returns the loss tensor (on device)."""
+    B = dev_in["view_img_fts"].shape[0]
+    pano = model("panorama", {"view_img_fts": dev_in["view_img_fts"], "view_lens": meta["view_lens"], "loc_fts": dev_in["loc_fts"],
+                              "nav_types": dev_in["nav_types"]})
+    pe = pano["pano_embeds"]
+    batch = {"data_type": ["r2r"] * B,
+             "vp_img_embeds": torch.cat([torch.zeros_like(pe[:, :1]), pe], 1),                    # mp3d_agent.py:268-270
+             "pano_masks": torch.ones((B, N_VIEWS + 1), dtype=torch.bool),                         # host mask (all views valid)
+             "vp_pos_fts": dev_in["vp_pos_fts"], "vp_cand_vpids": meta["vp_cand_vpids"],
+             "gmap_img_embeds": dev_in["gmap_img_embeds"], "gmap_step_ids": meta["gmap_step_ids"],
+             "gmap_pos_fts": dev_in["gmap_pos_fts"], "gmap_masks": meta["gmap_masks"], "gmap_pair_dists": None,
+             "gmap_visited_masks": meta["gmap_visited_masks"], "gmap_vpids": meta["gmap_vpids"],
+             "instruction": [""] * B, "history": [["h"] * N_HIST] * B,
+             "hist_vis": [list(dev_in["hist_vis"][b].unbind(0)) for b in range(B)], "prompts": meta["prompts"]}
+    if text is not None:
+        batch["text_input"] = text
+    out = model("navigation", batch)
+    loss = torch.nn.functional.cross_entropy(out["fuse_logits"].float(), dev_in["target_cols"], reduction="sum",
+                                             ignore_index=-100) / B                               # mp3d_agent.py:750
+    return loss
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (profiling recipe)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: oracle port of the reference on host cores (bounded sample)
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_layers: int, seq: int, reps: int = 1):
+    from oracle import navillm_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.OracleConfig(hidden=D_MODEL, n_layers=n_layers, n_heads=N_HEADS, inter=D_FF, vocab=64, precision="amp_bf16")
+    g = torch.Generator().manual_seed(0)
+    sd = {}
+    for l in range(n_layers):
+        p = f"lang_model.model.layers.{l}"
+        for nm, shp in (("self_attn.q_proj", (D_MODEL, D_MODEL)), ("self_attn.k_proj", (D_MODEL, D_MODEL)),
+                        ("self_attn.v_proj", (D_MODEL, D_MODEL)), ("self_attn.o_proj", (D_MODEL, D_MODEL)),
+                        ("mlp.gate_proj", (D_FF, D_MODEL)), ("mlp.up_proj", (D_FF, D_MODEL)), ("mlp.down_proj", (D_MODEL, D_FF))):
+            sd[f"{p}.{nm}.weight"] = torch.empty(shp, dtype=torch.bfloat16).normal_(0, 0.02, generator=g).requires_grad_(True)
+        sd[f"{p}.input_layernorm.weight"] = torch.ones(D_MODEL, dtype=torch.bfloat16, requires_grad=True)
+        sd[f"{p}.post_attention_layernorm.weight"] = torch.ones(D_MODEL, dtype=torch.bfloat16, requires_grad=True)
+    sd["lang_model.model.norm.weight"] = torch.ones(D_MODEL, dtype=torch.bfloat16, requires_grad=True)
+    emb = torch.randn(1, seq, D_MODEL, generator=g).to(torch.bfloat16).requires_grad_(True)
+    mask = torch.ones(1, seq, dtype=torch.long)
+    times = []
+    for _ in range(reps + 1):                                       # first pass = warm-up
+        t0 = time.perf_counter()
+        h = O.llama_model(sd, cfg, emb, mask)
+        h[:, -1].float().sum().backward()
+        times.append(time.perf_counter() - t0)
+    t_layers = min(times[1:]) if reps else times[0]
+    per_layer = t_layers / n_layers
+    t_step = per_layer * N_LAYERS                                    # pano encoder + heads are < 0.1 % of the FLOPs
+    return {"nav_steps_per_s": 1.0 / t_step, "seconds_per_step": t_step, "cores": cores,
+            "sample": f"oracle port (bf16 LM like the reference 'amp_bf16'), B=1, seq={seq} (workload mean length), "
+                      f"{n_layers} of {N_LAYERS} full-width Vicuna-7B layers fwd+bwd timed ({t_layers:.2f} s) and scaled x{N_LAYERS}/{n_layers}"}
+
+
+def run_reference_arm(a, rank, world):
+    if rank != 0:
+        return
+    mean_len = (LEN_LO + LEN_HI) // 2
+    vals = []
+    for _ in range(max(a.steps, 1)):
+        r = cpu_reference_sample(a.cpu_layers, mean_len, reps=1)
+        vals.append(r["nav_steps_per_s"])
+    v = statistics.median(vals)
+    line = {"impl": "reference", "metric": "nav_steps_per_sec", "value": v, "unit": "nav-steps/s", "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000.0 * B_STEP / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "C2 R2R-shaped training step (panorama+navigation fwd+bwd), B=16, 36x1408 views, hist=8, seq U{256..1024}, Vicuna-7B"},
+            "cpu_baseline": {"value": v, "unit": "nav-steps/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+            "e2e": {"value": v, "unit": "nav-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="nv", choices=["nv", "reference"])
+    ap.add_argument("--cpu-layers", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => number is INVALID")
+    a = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.impl == "reference":
+        run_reference_arm(a, rank, world)
+        return
+    assert a.warmup >= 3 or a.layers != N_LAYERS, "timing rule: at least 3 warm-up steps"
+
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from navillm_b200 import _lib, ops
+    if a.layers != N_LAYERS:
+        import navillm_b200.nav_model as nm
+        nm.VICUNA_7B["num_hidden_layers"] = a.layers
+    model = build_model(dev, seed=0)
+    host, meta = make_workload(1234 + rank)
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    tgt_pinned = meta["target_cols"].pin_memory()
+
+    def upload():
+        d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+        d["target_cols"] = tgt_pinned.to(dev, non_blocking=True)
+        return d
+
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pinned.values()) + tgt_pinned.numel() * 8
+    resident = upload()
+    text = model.lang_model.tokenize(meta["prompts"])
+    tokens_real = int(text["attention_mask"].sum())
+
+    def step_resident():
+        model.zero_grad(set_to_none=False)
+        loss = nav_step(model, resident, meta, dev, text=text)
+        loss.backward()
+        if world > 1:
+            model.allreduce_grads()
+        return loss
+
+    def step_e2e():
+        model.zero_grad(set_to_none=False)
+        d = upload()
+        loss = nav_step(model, d, meta, dev)          # tokenises the prompt strings on the host, like the reference
+        loss.backward()
+        if world > 1:
+            model.allreduce_grads()
+        return float(loss)                            # D2H read of the step's result
+
+    def timed(fn, k):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        st.record()
+        for _ in range(k):
+            fn()
+        en.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = st.elapsed_time(en)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
+    for _ in range(a.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count
+    ops.gemm_timer = []
+    with ClockSampler(local_rank) as clk:
+        ms = timed(step_resident, a.steps)
+    timer, ops.gemm_timer = ops.gemm_timer, None
+    launches = (_lib.launch_count - launches0) // max(a.steps, 1)
+    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in timer)
+    gemm_flops = sum(f for _, _, f in timer)
+    n_gemm = len(timer)
+
+    step_e2e()                                       # warm the e2e path (pinned staging, tokenizer caches)
+    ms_e2e = timed(step_e2e, a.steps)
+
+    if rank == 0:
+        pk = peaks()
+        value = world * B_STEP * a.steps / (ms / 1e3)
+        e2e = world * B_STEP * a.steps / (ms_e2e / 1e3)
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
+        # algorithmic FLOPs of the whole step on REAL (non-pad) tokens: 3 x (12.952 GF/token + attention)
+        lens = meta["lens"].astype(np.float64)
+        algo_step = 3.0 * float((lens * 12.952e9 + 0.262144e6 * lens * lens).sum()) + 3.0 * 2.229e9 * B_STEP
+        line = {
+            "metric": "nav_steps_per_sec", "value": value, "unit": "nav-steps/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "C2 R2R-shaped training step (panorama+navigation fwd+bwd), B=16/GPU, 36x1408 views, hist=8, "
+                                   "24 graph nodes, 15 candidates, seq U{256..1024} (packed: pad tokens not computed), Vicuna-7B random init",
+                       "layers": a.layers, "real_tokens_per_step": tokens_real, "l2": "inputs_exceed_l2 (13.5 GB of weights streamed per pass)",
+                       "grad_allreduce": "every step" if world > 1 else "n/a", "optimizer_step": "outside the boundary (train.py:86-89), not timed"},
+            "e2e": {"value": e2e, "unit": "nav-steps/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
+                    "ms_per_step": ms_e2e / a.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                         "frac": (achieved / pk["bf16_tflops"]) if achieved else None, "peak_src": pk["src"] + " (sustained cuBLAS bf16)",
+                         "launches_per_step": n_gemm // max(a.steps, 1), "share_of_step": gemm_ms / ms, "traffic": None,
+                         "step_algorithmic_tflop": algo_step / 1e12,
+                         "step_frac_of_peak": algo_step / 1e12 / (ms / a.steps / 1e3) / pk["bf16_tflops"]},
+            "clocks": clk.summary(),
+        }
+        if not a.no_cpu_baseline and world == 1:
+            r = cpu_reference_sample(a.cpu_layers, (LEN_LO + LEN_HI) // 2, reps=1)
+            line["cpu_baseline"] = {"value": r["nav_steps_per_s"], "unit": "nav-steps/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        if a.layers != N_LAYERS:
+            line["INVALID"] = f"debug run with {a.layers} layers"
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

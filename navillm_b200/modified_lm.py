@@ -140,7 +140,7 @@ class _LMFn(torch.autograd.Function):
         else:
             g, rstd, rows, shape, hn, dlogits = ctx.saved
             # dlogits was produced with scale 1/N; fold the incoming scalar gradient in on the device (no sync)
-            dlogits = (dlogits.float() * dout.float()).to(bf16)
+            dlogits.copy_(dlogits.float() * dout.float())        # in place: keeps the 16-byte-aligned row stride
             dy = ops.gemm(dlogits, lm.lm_head.weight.data, b_mn=True)                    # [Nl, D]
             ops.gemm(dlogits, hn, a_mn=True, b_mn=True, out=lm.lm_head.weight.grad, addend=lm.lm_head.weight.grad)
         dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)
