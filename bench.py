@@ -246,6 +246,7 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => number is INVALID")
+    ap.add_argument("--profile", action="store_true", help="for runs under ncu: no e2e / cpu arms, any warm-up count; the printed number is not a bench value")
     a = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -254,7 +255,7 @@ def main():
     if a.impl == "reference":
         run_reference_arm(a, rank, world)
         return
-    assert a.warmup >= 3 or a.layers != N_LAYERS, "timing rule: at least 3 warm-up steps"
+    assert a.warmup >= 3 or a.layers != N_LAYERS or a.profile, "timing rule: at least 3 warm-up steps"
 
     import torch.distributed as dist
     torch.cuda.set_device(local_rank)
@@ -297,7 +298,7 @@ def main():
         loss.backward()
         if world > 1:
             model.allreduce_grads()
-        return float(loss)                            # D2H read of the step's result
+        return float(loss.detach())                   # D2H read of the step's result
 
     def timed(fn, k):
         if world > 1:
@@ -331,6 +332,10 @@ def main():
     gemm_flops = sum(f for _, _, f in timer)
     n_gemm = len(timer)
 
+    if a.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / a.steps, "launches": int(launches)}))
+        return
     step_e2e()                                       # warm the e2e path (pinned staging, tokenizer caches)
     ms_e2e = timed(step_e2e, a.steps)
 

@@ -111,6 +111,21 @@ int nv_rows_combine(float* out, int64_t ldo, const float* A, int64_t lda, const 
 int nv_rows_scatter_add(float* dst, int64_t ldd, const int* idx, const float* src, int64_t lds, float alpha, int R, int D,
                         void* stream);
 
+/* ---- decode phase (csrc/decode.cu) --------------------------------------------------------------------------
+ * Pre-allocated contiguous KV cache ([B, Smax, H*128] bf16 per layer for K and V) + single-query attention +
+ * masked greedy argmax: replaces HF GenerationMixin's per-token torch.cat cache growth and eager attention
+ * (models/nav_model.py:324-338,388-399; models/modified_lm.py:184-199).  `lens` lives on the device so one decode
+ * step has static launch parameters (CUDA-graph replayable). */
+int nv_kv_store_prefill(const void* qkv, int64_t ld, const int* cu_seqlens, void* kcache, void* vcache, int B, int T,
+                        int Smax, int HD, void* stream);
+int nv_kv_append(const void* qkv, int64_t ld, const int* lens, void* kcache, void* vcache, int B, int Smax, int HD,
+                 void* stream);
+int nv_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* vcache, const int* lens, void* out,
+                   int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream);
+int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id,
+                     int pad_id, int stop_on_eos, int* next, int B, void* stream);
+int nv_add_int(int* x, int n, int delta, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

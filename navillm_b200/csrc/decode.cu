@@ -1,0 +1,222 @@
+// navillm_b200 — decode-phase kernels for greedy / sampled generation (HBM-bound regime).
+//
+// Replaces what the reference reaches through HF GenerationMixin.generate after the prefill
+// (models/nav_model.py:324-338,388-399; models/modified_lm.py:184-199): a tuple-of-tensors KV cache grown by
+// torch.cat every token and eager attention over it.  Here the cache is pre-allocated and contiguous
+// ([B, Smax, H*128] per layer for K and for V, bf16, real tokens only), one new token per sequence attends
+// over it with 128-bit coalesced loads, and the step has static shapes so the host can replay it as a CUDA
+// graph (sequence lengths live in device memory).
+#include "nv_common.cuh"
+#include "nv_host.h"
+
+namespace nv {
+
+__device__ __forceinline__ void unpack8d(const uint4& u, float (&f)[8]) {
+  f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
+  f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+}
+
+// Copy the K and V column blocks of packed prefill rows into the cache: row t of sequence b at local
+// position p goes to cache[b, p, :].
+__global__ void kv_store_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int* __restrict__ cu,
+                                        __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int Smax,
+                                        int HD) {
+  const int vecs = HD >> 3;
+  const int T = cu[B];
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)T * vecs;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int v = idx % vecs, t = idx / vecs;
+    int b = 0;
+    while (b + 1 < B && cu[b + 1] <= t) ++b;
+    const int p = t - cu[b];
+    if (p >= Smax) continue;
+    const int64_t dst = ((int64_t)b * Smax + p) * HD + v * 8;
+    *reinterpret_cast<uint4*>(kc + dst) = *reinterpret_cast<const uint4*>(qkv + (int64_t)t * ld + HD + v * 8);
+    *reinterpret_cast<uint4*>(vc + dst) = *reinterpret_cast<const uint4*>(qkv + (int64_t)t * ld + 2 * HD + v * 8);
+  }
+}
+
+// Append the new token's K,V (row b of qkv [B, 3*HD]) at position lens[b].
+__global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int* __restrict__ lens,
+                                 __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int Smax, int HD) {
+  const int vecs = HD >> 3;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < B * vecs; idx += gridDim.x * blockDim.x) {
+    const int v = idx % vecs, b = idx / vecs;
+    const int p = lens[b];
+    if (p >= Smax) continue;
+    const int64_t dst = ((int64_t)b * Smax + p) * HD + v * 8;
+    *reinterpret_cast<uint4*>(kc + dst) = *reinterpret_cast<const uint4*>(qkv + (int64_t)b * ld + HD + v * 8);
+    *reinterpret_cast<uint4*>(vc + dst) = *reinterpret_cast<const uint4*>(qkv + (int64_t)b * ld + 2 * HD + v * 8);
+  }
+}
+
+// One new query per sequence over its cache (keys 0..lens[b], the new token included: call after append).
+// CTA = (b, h), 4 warps; half-warps stream keys with 16-byte loads; per-warp online softmax, merged in smem.
+__global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
+                                                          const __nv_bfloat16* __restrict__ kc,
+                                                          const __nv_bfloat16* __restrict__ vc,
+                                                          const int* __restrict__ lens, __nv_bfloat16* __restrict__ out,
+                                                          int64_t ldo, int Smax, int H, float scale) {
+  __shared__ float s_m[4], s_l[4];
+  __shared__ float s_acc[4][128];
+  const int b = blockIdx.x / H, h = blockIdx.x % H;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, hl = lane & 15;          // half-warp id, lane within the half (8 dims each)
+  const int n = lens[b] + 1;                            // keys visible to the new token
+  const int HD = H * 128;
+  float qf[8];
+  unpack8d(*reinterpret_cast<const uint4*>(q + (int64_t)b * ldq + h * 128 + hl * 8), qf);
+  const float sl2 = scale * 1.4426950408889634f;
+  float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int j0 = w * 2; j0 < n; j0 += 8) {
+    const int j = j0 + half;
+    const bool ok = j < n;
+    float kf[8], vf[8];
+    float s = 0.f;
+    if (ok) {
+      const int64_t off = ((int64_t)b * Smax + j) * HD + h * 128 + hl * 8;
+      unpack8d(*reinterpret_cast<const uint4*>(kc + off), kf);
+      unpack8d(*reinterpret_cast<const uint4*>(vc + off), vf);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += qf[i] * kf[i];
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // reduce inside the half-warp
+    if (ok) {
+      const float mn = fmaxf(m, s);
+      const float a = exp2f((m - mn) * sl2), p = exp2f((s - mn) * sl2);
+      l = l * a + p;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = acc[i] * a + p * vf[i];
+      m = mn;
+    }
+  }
+  // merge the two half-warps
+  {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, 16), lo = __shfl_xor_sync(0xffffffffu, l, 16);
+    const float mn = fmaxf(m, mo);
+    const float a = (m == -INFINITY) ? 0.f : exp2f((m - mn) * sl2), ao = (mo == -INFINITY) ? 0.f : exp2f((mo - mn) * sl2);
+    l = l * a + lo * ao;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float other = __shfl_xor_sync(0xffffffffu, acc[i], 16);
+      acc[i] = acc[i] * a + other * ao;
+    }
+    m = mn;
+  }
+  if (lane < 16) {
+    if (lane == 0) { s_m[w] = m; s_l[w] = l; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s_acc[w][hl * 8 + i] = acc[i];
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    const int d = threadIdx.x;
+    float mm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float a = (s_m[k] == -INFINITY) ? 0.f : exp2f((s_m[k] - mm) * sl2);
+      num += s_acc[k][d] * a;
+      den += s_l[k] * a;
+    }
+    out[(int64_t)b * ldo + h * 128 + d] = __float2bfloat16_rn(num / den);
+  }
+}
+
+// next[b] = finished[b] ? pad_id : argmax_c logits[b,c] over non-special columns (first index wins ties, like
+// torch.argmax); finished[b] |= next == eos (when stop_on_eos).  One CTA per row.
+__global__ void __launch_bounds__(256) argmax_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int V,
+                                                     const int* __restrict__ special, int n_special,
+                                                     int* __restrict__ finished, int eos_id, int pad_id, int stop_on_eos,
+                                                     int* __restrict__ next) {
+  __shared__ float sv[256];
+  __shared__ int si[256];
+  const int b = blockIdx.x;
+  float best = -INFINITY;
+  int bi = V;
+  for (int c = threadIdx.x; c < V; c += blockDim.x) {
+    bool sp = false;
+    for (int s = 0; s < n_special; ++s) sp |= (special[s] == c);
+    if (sp) continue;
+    const float v = __bfloat162float(logits[(int64_t)b * ld + c]);
+    if (v > best) { best = v; bi = c; }   // strided scan keeps the smallest index per thread on ties
+  }
+  sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      const float v2 = sv[threadIdx.x + o];
+      const int i2 = si[threadIdx.x + o];
+      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) { sv[threadIdx.x] = v2; si[threadIdx.x] = i2; }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int tok = si[0];
+    if (finished[b]) tok = pad_id;
+    else if (stop_on_eos && tok == eos_id) finished[b] = 1;
+    next[b] = tok;
+  }
+}
+
+__global__ void add_int_kernel(int* __restrict__ x, int n, int delta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] += delta;
+}
+
+}  // namespace nv
+
+using namespace nv;
+#define S_(x) reinterpret_cast<cudaStream_t>(x)
+#define BF(x) reinterpret_cast<__nv_bfloat16*>(x)
+#define CBF(x) reinterpret_cast<const __nv_bfloat16*>(x)
+
+extern "C" {
+
+int nv_kv_store_prefill(const void* qkv, int64_t ld, const int* cu_seqlens, void* kcache, void* vcache, int B, int T,
+                        int Smax, int HD, void* stream) {
+  if (T == 0) return NV_OK;
+  NV_REQUIRE((HD & 7) == 0 && (ld & 7) == 0, "nv_kv_store_prefill: alignment");
+  const int64_t work = (int64_t)T * (HD >> 3);
+  int grid = (int)((work + 255) / 256);
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+  kv_store_prefill_kernel<<<grid, 256, 0, S_(stream)>>>(CBF(qkv), ld, cu_seqlens, BF(kcache), BF(vcache), B, Smax, HD);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_kv_append(const void* qkv, int64_t ld, const int* lens, void* kcache, void* vcache, int B, int Smax, int HD,
+                 void* stream) {
+  if (B == 0) return NV_OK;
+  kv_append_kernel<<<(B * (HD >> 3) + 255) / 256, 256, 0, S_(stream)>>>(CBF(qkv), ld, lens, BF(kcache), BF(vcache), B, Smax, HD);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* vcache, const int* lens, void* out,
+                   int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream) {
+  NV_REQUIRE(head_dim == 128, "nv_decode_attn: head_dim must be 128");
+  if (B == 0) return NV_OK;
+  decode_attn_kernel<<<B * H, 128, 0, S_(stream)>>>(CBF(q), ldq, CBF(kcache), CBF(vcache), lens, BF(out), ldo, Smax, H, scale);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id,
+                     int pad_id, int stop_on_eos, int* next, int B, void* stream) {
+  if (B == 0) return NV_OK;
+  argmax_kernel<<<B, 256, 0, S_(stream)>>>(CBF(logits), ld, V, special, n_special, finished, eos_id, pad_id, stop_on_eos, next);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_add_int(int* x, int n, int delta, void* stream) {
+  if (n == 0) return NV_OK;
+  add_int_kernel<<<(n + 255) / 256, 256, 0, S_(stream)>>>(x, n, delta);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+}  // extern "C"

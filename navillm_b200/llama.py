@@ -205,7 +205,7 @@ class LlamaCore:
         self.cos, self.sin = rope_tables(dims, flat.flat.device)
 
     # -------------------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True):
+    def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True, kv_sink=None):
         """x: [T, D] bf16 input embeddings (packed); pos: int32 [T]; cu: int32 [B+1] (device); seqlens: host
         lengths.  Returns (residual stream after the last layer BEFORE the final RMSNorm, tape) where ``tape``
         holds the per-layer activations for ``backward`` (None when save=False).  The tape travels with the
@@ -219,6 +219,8 @@ class LlamaCore:
             s.xn, s.rstd1 = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
             s.qkv = ops.gemm(s.xn, self.wqkv[l])
             ops.rope_(s.qkv, pos, self.cos, self.sin, 2 * H, d.head_dim)
+            if kv_sink is not None:
+                kv_sink(l, s.qkv)                      # prefill of generate(): post-RoPE K,V go to the cache
             s.ao, s.lse = ops.attn_fwd(s.qkv, cu, seqlens, H)
             s.xm = ops.gemm(s.ao, self.wo[l], addend=x)
             s.xn2, s.rstd2 = ops.rmsnorm_fwd(s.xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
@@ -265,3 +267,25 @@ class LlamaCore:
             del dxn, dxm
             saved[l] = None
         return dx
+
+
+    # -------------------------------------------------------------------------------------------------
+    def decode_step(self, x: torch.Tensor, lens: torch.Tensor, kc: List[torch.Tensor], vc: List[torch.Tensor]) -> torch.Tensor:
+        """One new token per sequence.  x: [B, D] bf16 embeddings of the new tokens; lens: int32 [B] (device) =
+        number of cached tokens = position of the new token; caches [B, Smax, D] per layer.  Static shapes and
+        device-resident lengths: the whole step can be captured in a CUDA graph.  Returns the residual stream
+        [B, D] before the final RMSNorm."""
+        d = self.d
+        H, D = d.n_heads, d.hidden
+        for l, lyr in enumerate(self.model.layers):
+            xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
+            qkv = ops.gemm(xn, self.wqkv[l], block_n=128)
+            ops.rope_(qkv, lens, self.cos, self.sin, 2 * H, d.head_dim)
+            ops.kv_append(qkv, lens, kc[l], vc[l])
+            ao = ops.decode_attn(qkv, kc[l], vc[l], lens, H)
+            xm = ops.gemm(ao, self.wo[l], addend=x, block_n=128)
+            xn2, _ = ops.rmsnorm_fwd(xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
+            gu = ops.gemm(xn2, self.wgu[l], block_n=128)
+            h = ops.swiglu_fwd(gu)
+            x = ops.gemm(h, self.wd[l], addend=xm, block_n=128)
+        return x

@@ -304,3 +304,112 @@ class ModifiedLlamaForCausalLM(nn.Module):
                 lg[:, self.special_token_ids] = float("-inf")
                 logits = torch.zeros((pp.B * pp.S, lg.shape[1]), dtype=bf16, device=dev).index_copy(0, flat, lg).view(pp.B, pp.S, -1)
         return LMOutput(loss=loss, logits=logits, past_key_values=None, hidden_states=hidden, attentions=None)
+
+
+    # ---- generation (models/nav_model.py:324-338,388-399; HF GenerationMixin greedy / sampling) ----
+    @torch.no_grad()
+    def generate(self, input_ids, attention_mask, cand_vis=None, hist_vis=None, obj_vis=None, max_new_tokens: int = 20,
+                 do_sample: bool = False, temperature: float = 1.0, eos_token_id: Optional[int] = None,
+                 pad_token_id: Optional[int] = None, bos_token_id: Optional[int] = None, logits_processor=None, trie=None,
+                 stop_on_eos: bool = True, use_cuda_graph: bool = True, **unused) -> torch.Tensor:
+        """Prefill on the packed kernels (positions = cumsum(mask)-1 like HF generate; visual tokens injected only
+        here, as in models/modified_lm.py:195-197), then one token per step over a pre-allocated KV cache.  The
+        greedy step has static shapes and is replayed as a CUDA graph.  Returns [B, S0 + n_new] int64 ids (prompt
+        part copied from the input; finished rows continue with pad_token_id like HF greedy search)."""
+        self._ensure()
+        dev = self._device()
+        core, d = self.core, self.dims
+        eos = self.tokenizer.eos_token_id if eos_token_id is None else eos_token_id
+        pad = self.tokenizer.unk_token_id if pad_token_id is None else pad_token_id
+        pp = PackedPrompt(input_ids, attention_mask, self, dev, generate_positions=True)
+        vis = self.cat_vis(cand_vis, hist_vis, obj_vis, pp)
+        B, H, D = pp.B, d.n_heads, d.hidden
+        Smax = (max(pp.seqlens) + max_new_tokens + 63) // 64 * 64
+        kc = [torch.empty((B, Smax, D), dtype=bf16, device=dev) for _ in range(d.n_layers)]
+        vc = [torch.empty((B, Smax, D), dtype=bf16, device=dev) for _ in range(d.n_layers)]
+
+        def sink(l, qkv):
+            ops.kv_store_prefill(qkv, pp.cu, kc[l], vc[l], B, pp.T)
+
+        E = self.model.embed_tokens.weight.data
+        x = ops.embed_fwd(pp.ids, E, pp.vis_src if vis is not None else None, vis)
+        hid, _ = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=False, kv_sink=sink)
+        V = self.lm_head.weight.shape[0]
+        Vp = (V + 63) // 64 * 64
+        logits = torch.empty((B, Vp), dtype=bf16, device=dev)[:, :V]
+        next_ids = torch.empty((B,), dtype=torch.int32, device=dev)
+        finished = torch.zeros((B,), dtype=torch.int32, device=dev)
+        lens = torch.tensor(pp.seqlens, dtype=torch.int32, device=dev)
+        special = self.special_ids_dev
+        greedy = (not do_sample) and trie is None and not logits_processor
+
+        def head(h_rows):
+            hn, _ = ops.rmsnorm_fwd(h_rows, self.model.norm.weight.data, d.rms_eps)
+            ops.gemm(hn, self.lm_head.weight.data, out=logits, block_n=128)
+
+        trie_state = [None]
+
+        def pick(all_ids_host):
+            """next token from `logits` -> next_ids (device)."""
+            if greedy:
+                ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)
+                return
+            lg = logits.float()
+            lg[:, self.special_token_ids] = float("-inf")
+            if trie is not None:                                  # TrieLogitsProcessor (models/modified_lm.py:10-30)
+                if trie_state[0] is None:
+                    trie_state[0] = [trie.root for _ in range(B)]
+                else:
+                    for bn in range(B):
+                        trie_state[0][bn] = trie.get_next_node(trie_state[0][bn], int(all_ids_host[bn][-1]))
+                allow = torch.zeros_like(lg, dtype=torch.bool)
+                for bn in range(B):
+                    allow[bn, trie.get_child_index(trie_state[0][bn])] = True
+                lg = lg.masked_fill(~allow, float("-inf"))
+            for proc in (logits_processor or []):
+                lg = proc(torch.tensor(all_ids_host, device=dev), lg)
+            if do_sample:
+                nxt = torch.multinomial(torch.softmax(lg / max(temperature, 1e-6), dim=-1), 1).squeeze(1)
+            else:
+                nxt = lg.argmax(dim=-1)
+            fin = finished.bool()
+            nxt = torch.where(fin, torch.full_like(nxt, pad), nxt)
+            if stop_on_eos:
+                finished.copy_((fin | (nxt == eos)).to(torch.int32))
+            next_ids.copy_(nxt.to(torch.int32))
+
+        head(ops.gather_rows(hid, pp.last_rows))
+        host_ids = [row.tolist() for row in input_ids.cpu()]
+        pick(host_ids)
+        out_tokens = [next_ids.clone()]
+
+        def step():
+            xt = ops.embed_fwd(next_ids, E)
+            h = core.decode_step(xt, lens, kc, vc)
+            head(h)
+            ops.add_int_(lens, 1)
+
+        graph = None
+        for it in range(1, max_new_tokens):
+            if stop_on_eos and bool(finished.all()):              # HF stops when every sequence has finished
+                break
+            if not greedy:
+                for bn, t in enumerate(out_tokens[-1].tolist()):
+                    host_ids[bn].append(t)
+            if greedy and use_cuda_graph:
+                if graph is None:
+                    step(); ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)   # warm-up (eager)
+                    out_tokens.append(next_ids.clone())
+                    graph = torch.cuda.CUDAGraph()
+                    torch.cuda.synchronize()
+                    with torch.cuda.graph(graph):
+                        step()
+                        ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)
+                    continue
+                graph.replay()
+            else:
+                step()
+                pick(host_ids)
+            out_tokens.append(next_ids.clone())
+        new = torch.stack(out_tokens, dim=1).to(torch.int64)
+        return torch.cat([input_ids.to(dev), new], dim=1)

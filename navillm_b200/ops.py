@@ -389,3 +389,44 @@ def logit_scatter_bwd(dout, slot, O):
     check(_lib.load().nv_logit_scatter_bwd(ptr(dout), ptr(slot), ptr(dpred), i32(O), i32(B), i32(G), stream_ptr()),
           "nv_logit_scatter_bwd")
     return dpred
+
+
+# ---------------------------------------------------------------------------------------------------
+# decode-phase kernels (csrc/decode.cu)
+# ---------------------------------------------------------------------------------------------------
+def kv_store_prefill(qkv, cu, kc, vc, B, T):
+    Smax, HD = kc.shape[1], kc.shape[2]
+    check(_lib.load().nv_kv_store_prefill(ptr(qkv), i64(qkv.stride(0)), ptr(cu), ptr(kc), ptr(vc), i32(B), i32(T), i32(Smax),
+                                          i32(HD), stream_ptr()), "nv_kv_store_prefill")
+
+
+def kv_append(qkv, lens, kc, vc):
+    B, Smax, HD = kc.shape
+    check(_lib.load().nv_kv_append(ptr(qkv), i64(qkv.stride(0)), ptr(lens), ptr(kc), ptr(vc), i32(B), i32(Smax), i32(HD),
+                                   stream_ptr()), "nv_kv_append")
+
+
+def decode_attn(q, kc, vc, lens, n_heads, *, out=None, scale=None):
+    """q: [B, >=H*128] bf16 view (first H*128 columns used); caches [B, Smax, H*128]; lens: int32 [B] = index of the
+    new token (already appended).  Returns [B, H*128] bf16."""
+    B, Smax, HD = kc.shape
+    if out is None:
+        out = torch.empty((B, HD), dtype=bf16, device=q.device)
+    if scale is None:
+        scale = 128 ** -0.5
+    check(_lib.load().nv_decode_attn(ptr(q), i64(q.stride(0)), ptr(kc), ptr(vc), ptr(lens), ptr(out), i64(out.stride(0)),
+                                     i32(B), i32(Smax), i32(n_heads), i32(128), f32(scale), stream_ptr()), "nv_decode_attn")
+    return out
+
+
+def argmax_masked(logits, special, finished, eos_id, pad_id, stop_on_eos, next_ids):
+    B, V = logits.shape
+    check(_lib.load().nv_argmax_masked(ptr(logits), i64(logits.stride(0)), i32(V), ptr(special), i32(special.numel()),
+                                       ptr(finished), i32(eos_id), i32(pad_id), i32(1 if stop_on_eos else 0), ptr(next_ids),
+                                       i32(B), stream_ptr()), "nv_argmax_masked")
+    return next_ids
+
+
+def add_int_(x, delta):
+    check(_lib.load().nv_add_int(ptr(x), i32(x.numel()), i32(delta), stream_ptr()), "nv_add_int")
+    return x
