@@ -168,6 +168,25 @@ class FlatParams:
         return self.flat_grad[o:o + numel].view(shape)
 
 
+def allreduce_flat_grads(flats, average: bool = True) -> int:
+    """Data-parallel gradient exchange of the path: ONE all-reduce per flat gradient buffer
+    (bf16 LM+heads, fp32 encoder/embeddings) instead of DDP's per-bucket reductions (tools/optims.py:52-54).
+    Returns the number of collectives issued (0 without an initialised multi-rank process group)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 0
+    ws = dist.get_world_size()
+    n = 0
+    for flat in flats:
+        if flat is None:
+            continue
+        dist.all_reduce(flat.flat_grad)
+        if average:
+            flat.flat_grad.div_(ws)
+        n += 1
+    return n
+
+
 def rope_tables(d: LlamaDims, device) -> tuple:
     """cos/sin [max_pos, head_dim] in bf16, built exactly like HF LlamaRotaryEmbedding (fp32 cos/sin of
     pos * inv_freq, concatenated halves, cast to the model dtype)."""

@@ -251,16 +251,8 @@ class NavModel(nn.Module):
     def allreduce_grads(self, average: bool = True):
         """ONE NCCL all-reduce per dtype over the flat gradient buffers (replaces DDP's
         bucketed reduction of tools/optims.py:52-54).  No-op without an initialised process group."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return
-        ws = dist.get_world_size()
-        for flat in (self.lang_model.flat, self._flat32):
-            if flat is None:
-                continue
-            dist.all_reduce(flat.flat_grad)
-            if average:
-                flat.flat_grad.div_(ws)
+        from .llama import allreduce_flat_grads
+        return allreduce_flat_grads([self.lang_model.flat, self._flat32], average=average)
 
     def _anchor_t(self):
         return self._anchor.detach().requires_grad_(torch.is_grad_enabled())
