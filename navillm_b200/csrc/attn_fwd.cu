@@ -7,40 +7,43 @@
 // cu_seqlens[b+1]; the reference's left padding is reproduced by the explicit position ids given to
 // the rotary kernel, so results at real tokens are identical (pad positions do not exist here).
 //
-// One CTA = one (128-query block, head).  head_dim = 128.
-//   warp 0 (1 lane)  TMA producer: Q once, then K_j / V_j tiles through a 2-stage ring
-//   warp 1 (1 lane)  tcgen05.mma issuer: S = Q K_j^T (fp32 in TMEM), O += P V_j
-//   warps 2..5       one thread per query row: tcgen05.ld S -> online softmax (exp2, fp32) -> P (bf16)
-//                    into 128B-swizzled smem as the next MMA's A operand; rescales O in TMEM when the
-//                    running max moved; final O / l -> bf16 -> HBM, LSE -> HBM (for the backward)
-// TMEM: S cols [0,128), O cols [128,256).  smem: Q 32K + 2x(K 32K + V 32K) + P 32K = 192 KB.
+// One CTA = one (256-query block = two 128-row tiles, head).  head_dim = 128.  The two tiles ping-pong so
+// that the tensor pipe (S = QK^T, O += PV) and the MUFU-bound softmax of the other tile overlap:
+//   warp 0 (1 lane)   TMA producer: Q0,Q1 once; K_j (1 stage) and V_j (2 stages) per 128-key block
+//   warp 1 (1 lane)   tcgen05.mma issuer; issue order per key block: S_0(j+1), PV_0(j), S_1(j+1), PV_1(j)
+//   warps 2..5 / 6..9 softmax group of tile 0 / tile 1, one thread per query row: tcgen05.ld S -> online
+//                     softmax (exp2, fp32) -> P (bf16) into 128B-swizzled smem (the next MMA's A operand);
+//                     rescales O in TMEM when the running max moved; final O / l -> bf16, LSE -> HBM
+// TMEM: S0 [0,128) S1 [128,256) O0 [256,384) O1 [384,512).
+// smem: Q 2x32K + K 32K + V 2x32K + P 2x32K = 224 KB.
 #include "nv_common.cuh"
 #include "nv_host.h"
 
 namespace nv {
 
-constexpr uint32_t ATT_BM = 128, ATT_BN = 128, ATT_HD = 128;
 constexpr uint32_t ATT_TILE_BYTES = 128 * 128 * 2;  // one 128x128 bf16 tile = two 64-wide swizzle atoms
 constexpr uint32_t ATT_ATOM_BYTES = 128 * 128;      // 128 rows x 128 B
-constexpr uint32_t ATT_THREADS = 192;
+constexpr uint32_t ATT_THREADS = 320;
+constexpr uint32_t ATT_QROWS = 256;
 
 struct AttnFwdSmem {
-  static constexpr uint32_t Q_OFF = 0;
-  static constexpr uint32_t K_OFF = Q_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t V_OFF = K_OFF + 2 * ATT_TILE_BYTES;
-  static constexpr uint32_t P_OFF = V_OFF + 2 * ATT_TILE_BYTES;
-  static constexpr uint32_t BAR_OFF = P_OFF + ATT_TILE_BYTES;
-  static constexpr uint32_t NUM_BARS = 8;  // q_full, kv_full[2], kv_empty[2], s_full, p_ready, pv_done
+  static constexpr uint32_t Q_OFF = 0;                          // 2 tiles
+  static constexpr uint32_t K_OFF = Q_OFF + 2 * ATT_TILE_BYTES;  // 1 stage
+  static constexpr uint32_t V_OFF = K_OFF + ATT_TILE_BYTES;      // 2 stages
+  static constexpr uint32_t P_OFF = V_OFF + 2 * ATT_TILE_BYTES;  // 2 tiles
+  static constexpr uint32_t BAR_OFF = P_OFF + 2 * ATT_TILE_BYTES;
+  // q_full, k_full, k_empty, v_full[2], v_empty[2], s_full[2], p_ready[2], pv_done[2]
+  static constexpr uint32_t NUM_BARS = 13;
   static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
   static constexpr uint32_t DYN_BYTES = TOTAL + 1024;
 };
 
-// Map a flat (reversed, so the longest causal blocks start first) block id to (sequence, q-block).
-__device__ __forceinline__ bool locate_block(const int* __restrict__ cu, int B, uint32_t blk, int& seq_start,
-                                             int& seq_len, uint32_t& qblk) {
+// Map a flat block id to (sequence, 256-row query block); heavy (late) blocks are launched first.
+__device__ __forceinline__ bool locate_qblock(const int* __restrict__ cu, int B, uint32_t blk, int& seq_start,
+                                              int& seq_len, uint32_t& qblk) {
   for (int b = 0; b < B; ++b) {
     const int s = cu[b], len = cu[b + 1] - s;
-    const uint32_t nb = (len + ATT_BM - 1) / ATT_BM;
+    const uint32_t nb = (len + ATT_QROWS - 1) / ATT_QROWS;
     if (blk < nb) { seq_start = s; seq_len = len; qblk = blk; return true; }
     blk -= nb;
   }
@@ -60,11 +63,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint8_t* sP = smem + L::P_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = bars + 3;
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_ready = bars + 6;
-  uint64_t* pv_done = bars + 7;
+  uint64_t* k_full = bars + 1;
+  uint64_t* k_empty = bars + 2;
+  uint64_t* v_full = bars + 3;    // [2]
+  uint64_t* v_empty = bars + 5;   // [2]
+  uint64_t* s_full = bars + 7;    // [2] per tile
+  uint64_t* p_ready = bars + 9;   // [2]
+  uint64_t* pv_done = bars + 11;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,143 +77,164 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   int seq_start = 0, seq_len = 0;
   uint32_t qblk = 0;
-  const bool ok = locate_block(cu_seqlens, B, gridDim.x - 1 - blockIdx.x, seq_start, seq_len, qblk);
-  if (!ok) return;  // uniform across the CTA
-  const uint32_t nkv = qblk + 1;  // causal: key blocks 0..qblk
+  if (!locate_qblock(cu_seqlens, B, gridDim.x - 1 - blockIdx.x, seq_start, seq_len, qblk)) return;  // CTA-uniform
+  const uint32_t q0 = qblk * ATT_QROWS;                         // first query row (inside the sequence)
+  const bool tile1_on = (q0 + 128) < (uint32_t)seq_len;         // second tile has at least one real row
+  // key blocks: tile 0 sees blocks 0..2*qblk, tile 1 sees 0..2*qblk+1
+  const uint32_t n_blocks = tile1_on ? 2 * qblk + 2 : 2 * qblk + 1;
+  auto tile_on = [&](uint32_t t, uint32_t j) -> bool { return t == 0 ? (j <= 2 * qblk) : (tile1_on && j <= 2 * qblk + 1); };
+  auto last_tile = [&](uint32_t j) -> uint32_t { return tile_on(1, j) ? 1u : 0u; };
+  auto first_tile = [&](uint32_t j) -> uint32_t { return tile_on(0, j) ? 0u : 1u; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 128);
-    mbar_init(pv_done, 1);
+    mbar_init(k_full, 1); mbar_init(k_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_ready[i], 128); mbar_init(&pv_done[i], 1);
+    }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 256); tmem_relinquish(); }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
 
   if (warp == 0) {
+    // ================================ TMA producer ================================
     if (lane == 0) {
-      const int32_t qrow0 = seq_start + qblk * ATT_BM;
-      const int32_t qcol = head * ATT_HD;
-      mbar_arrive_expect_tx(q_full, ATT_TILE_BYTES);
-      tma_load_2d(sQ, &tmap_q, q_full, qcol, qrow0);
-      tma_load_2d(sQ + ATT_ATOM_BYTES, &tmap_q, q_full, qcol + 64, qrow0);
-      for (uint32_t j = 0; j < nkv; ++j) {
-        const uint32_t st = j & 1, n = j >> 1;
-        mbar_wait(&kv_empty[st], (n & 1) ^ 1);
-        mbar_arrive_expect_tx(&kv_full[st], 2 * ATT_TILE_BYTES);
-        const int32_t krow0 = seq_start + j * ATT_BN;
-        uint8_t* k = sK + st * ATT_TILE_BYTES;
-        uint8_t* v = sV + st * ATT_TILE_BYTES;
-        tma_load_2d(k, &tmap_k, &kv_full[st], qcol, krow0);
-        tma_load_2d(k + ATT_ATOM_BYTES, &tmap_k, &kv_full[st], qcol + 64, krow0);
-        tma_load_2d(v, &tmap_v, &kv_full[st], qcol, krow0);
-        tma_load_2d(v + ATT_ATOM_BYTES, &tmap_v, &kv_full[st], qcol + 64, krow0);
+      const int32_t qcol = head * 128;
+      const int32_t qrow0 = seq_start + q0;
+      mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        tma_load_2d(sQ + t * ATT_TILE_BYTES, &tmap_q, q_full, qcol, qrow0 + t * 128);
+        tma_load_2d(sQ + t * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmap_q, q_full, qcol + 64, qrow0 + t * 128);
+      }
+      for (uint32_t j = 0; j < n_blocks; ++j) {
+        const int32_t krow0 = seq_start + j * 128;
+        mbar_wait(k_empty, (j & 1) ^ 1);
+        mbar_arrive_expect_tx(k_full, ATT_TILE_BYTES);
+        tma_load_2d(sK, &tmap_k, k_full, qcol, krow0);
+        tma_load_2d(sK + ATT_ATOM_BYTES, &tmap_k, k_full, qcol + 64, krow0);
+        const uint32_t st = j & 1;
+        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
+        tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], qcol, krow0);
+        tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmap_v, &v_full[st], qcol + 64, krow0);
       }
     }
   } else if (warp == 1) {
+    // ================================ MMA issuer ================================
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // P (K-major) x V (MN-major: hd contiguous)
-      auto issue_s = [&](uint32_t j) {
-        const uint32_t st = j & 1;
-        mbar_wait(&kv_full[st], (j >> 1) & 1);
-        tc_fence_after();
+      auto issue_s = [&](uint32_t t) {
 #pragma unroll
         for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t ad = umma_smem_desc_sw128(smem_u32(sQ + ka * ATT_ATOM_BYTES), 0, 1024);
-          const uint64_t bd = umma_smem_desc_sw128(smem_u32(sK + st * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024);
+          const uint64_t ad = umma_smem_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024);
+          const uint64_t bd = umma_smem_desc_sw128(smem_u32(sK + ka * ATT_ATOM_BYTES), 0, 1024);
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_S, ad + ks * 2, bd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_f16_ss(tmem_base + t * 128, ad + ks * 2, bd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
         }
-        umma_commit(s_full);
+        umma_commit(&s_full[t]);
       };
-      mbar_wait(q_full, 0);
-      issue_s(0);
-      for (uint32_t j = 0; j < nkv; ++j) {
-        const uint32_t st = j & 1;
-        mbar_wait(p_ready, j & 1);
-        tc_fence_after();
-        if (j + 1 < nkv) issue_s(j + 1);  // S_{j+1} runs on the tensor core while the row threads finish P_j's tail
+      auto issue_pv = [&](uint32_t t, uint32_t st, bool accumulate) {
 #pragma unroll
         for (uint32_t ka = 0; ka < 2; ++ka) {
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = umma_smem_desc_sw128(smem_u32(sP + ka * ATT_ATOM_BYTES), 0, 1024) + ks * 2;
+            const uint64_t ad = umma_smem_desc_sw128(smem_u32(sP + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024) + ks * 2;
             // V tile: rows = keys (K dim), 128 B of hd per row per atom; atoms (hd halves) ATT_ATOM_BYTES apart
             const uint64_t bd = umma_smem_desc_sw128(
                 smem_u32(sV + st * ATT_TILE_BYTES + (ka * 64 + ks * 16) * 128), ATT_ATOM_BYTES, 1024);
-            umma_f16_ss(tmem_O, ad, bd, idesc_pv, (j | ka | ks) ? 1u : 0u);
+            umma_f16_ss(tmem_base + 256 + t * 128, ad, bd, idesc_pv, (accumulate || (ka | ks)) ? 1u : 0u);
           }
         }
-        umma_commit(&kv_empty[st]);
-        umma_commit(pv_done);
+        umma_commit(&pv_done[t]);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full, 0);
+      tc_fence_after();
+      for (uint32_t t = 0; t < 2; ++t)
+        if (tile_on(t, 0)) issue_s(t);
+      umma_commit(k_empty);
+      for (uint32_t j = 0; j < n_blocks; ++j) {
+        const uint32_t st = j & 1;
+        const bool have_next = (j + 1 < n_blocks);
+        bool k_next_waited = false, v_waited = false;
+        for (uint32_t t = 0; t < 2; ++t) {
+          if (!tile_on(t, j)) continue;
+          mbar_wait(&p_ready[t], j & 1);           // tile t processes every block 0..its last, so its phase index is j
+          tc_fence_after();
+          if (have_next && tile_on(t, j + 1)) {
+            if (!k_next_waited) { mbar_wait(k_full, (j + 1) & 1); tc_fence_after(); k_next_waited = true; }
+            issue_s(t);                             // S_t(j+1) overlaps the other tile's softmax
+            if (t == last_tile(j + 1)) umma_commit(k_empty);
+          }
+          if (!v_waited) { mbar_wait(&v_full[st], (j >> 1) & 1); tc_fence_after(); v_waited = true; }
+          issue_pv(t, st, j > 0);
+          if (t == last_tile(j)) umma_commit(&v_empty[st]);
+        }
+        // a block seen only by tile 1 whose S could not be issued from tile 0's branch: handled above because
+        // tile_on(1, j+1) implies tile_on(1, j); tile 0 dropping out at the last block needs no S.
       }
     }
   } else {
-    // ---- one thread per query row ----
+    // ================================ softmax groups ================================
+    const uint32_t t = (warp - 2) >> 2;                   // tile of this group
     const uint32_t quarter = warp & 3;
-    const uint32_t r = quarter * 32 + lane;              // row inside the q block
-    const uint32_t lane_off = (quarter * 32) << 16;      // TMEM lane field
+    const uint32_t r = quarter * 32 + lane;               // row inside the tile
+    const uint32_t lane_off = (quarter * 32) << 16;       // TMEM lane field
+    const uint32_t tmem_S = tmem_base + t * 128, tmem_O = tmem_base + 256 + t * 128;
+    uint8_t* sPt = sP + t * ATT_TILE_BYTES;
     const float sl2 = scale * 1.4426950408889634f;
+    const uint32_t my_blocks = (t == 0) ? (2 * qblk + 1) : (tile1_on ? 2 * qblk + 2 : 0);
+    const uint32_t diag_blk = 2 * qblk + t;
     float m_run = -INFINITY, l_run = 0.f;
-    for (uint32_t j = 0; j < nkv; ++j) {
-      mbar_wait(s_full, j & 1);
+    for (uint32_t j = 0; j < my_blocks; ++j) {
+      mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      const bool diag = (j == qblk);
-      // pass 1: row max
+      const bool diag = (j == diag_blk);
+      // whole S row -> registers (4 x 32 columns), one wait
+      uint32_t s[128];
+      tmem_ld_32x32b_x32(tmem_S + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
+      tmem_ld_32x32b_x32(tmem_S + lane_off + 32, *reinterpret_cast<uint32_t(*)[32]>(&s[32]));
+      tmem_ld_32x32b_x32(tmem_S + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
+      tmem_ld_32x32b_x32(tmem_S + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
+      tmem_ld_wait();
       float m_new = m_run;
-#pragma unroll 1
-      for (uint32_t c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + c, v);
-        tmem_ld_wait();
 #pragma unroll
-        for (uint32_t i = 0; i < 32; ++i) {
-          const float s = __uint_as_float(v[i]);
-          if (!diag || c + i <= r) m_new = fmaxf(m_new, s);
-        }
-      }
+      for (uint32_t i = 0; i < 128; ++i)
+        if (!diag || i <= r) m_new = fmaxf(m_new, __uint_as_float(s[i]));
       const float alpha = exp2f((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1);  // P buffer and O accumulator free again
-      tc_fence_after();
-      // pass 2: p = exp2(s*sl2 - m*sl2) -> bf16 -> swizzled smem; row sum
       float rs = 0.f;
-#pragma unroll 1
-      for (uint32_t c = 0; c < 128; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + c, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
 #pragma unroll
-        for (uint32_t i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(v[i]) * sl2 - mb);
-          float p1 = exp2f(__uint_as_float(v[i + 1]) * sl2 - mb);
-          if (diag) {
-            if (c + i > r) p0 = 0.f;
-            if (c + i + 1 > r) p1 = 0.f;
-          }
-          // the row sum uses the bf16-rounded probabilities that the PV product actually consumes
-          pk[i >> 1] = pack_bf16x2(p0, p1);
-          rs += bf16_lo(pk[i >> 1]) + bf16_hi(pk[i >> 1]);
+      for (uint32_t i = 0; i < 128; i += 2) {
+        float p0 = exp2f(__uint_as_float(s[i]) * sl2 - mb);
+        float p1 = exp2f(__uint_as_float(s[i + 1]) * sl2 - mb);
+        if (diag) {
+          if (i > r) p0 = 0.f;
+          if (i + 1 > r) p1 = 0.f;
         }
-        uint8_t* atom = sP + (c >> 6) * ATT_ATOM_BYTES;
-        const uint32_t chunk0 = (c & 63) >> 3;
+        // the row sum uses the bf16-rounded probabilities that the PV product actually consumes
+        const uint32_t pk = pack_bf16x2(p0, p1);
+        s[i >> 1] = pk;
+        rs += bf16_lo(pk) + bf16_hi(pk);
+      }
+      if (j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);   // P_t buffer and O_t accumulator free again
+      tc_fence_after();
 #pragma unroll
-        for (uint32_t q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(atom + sw128_offset(r, chunk0 + q)) =
-              make_uint4(pk[q * 4], pk[q * 4 + 1], pk[q * 4 + 2], pk[q * 4 + 3]);
+      for (uint32_t c = 0; c < 16; ++c) {                // 16 chunks of 8 bf16 (16 B)
+        uint8_t* atom = sPt + (c >> 3) * ATT_ATOM_BYTES;
+        *reinterpret_cast<uint4*>(atom + sw128_offset(r, c & 7)) = make_uint4(s[c * 4], s[c * 4 + 1], s[c * 4 + 2], s[c * 4 + 3]);
       }
       l_run = l_run * alpha + rs;
       m_run = m_new;
-      // rescale the O accumulator when some row of this warp moved its max
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.f)) {
 #pragma unroll 1
         for (uint32_t c = 0; c < 128; c += 32) {
@@ -223,46 +249,49 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
       fence_proxy_async_smem();  // P stores (generic proxy) -> visible to tcgen05.mma (async proxy)
       tc_fence_before();
-      mbar_arrive(p_ready);
+      mbar_arrive(&p_ready[t]);
     }
     // ---- epilogue ----
-    mbar_wait(pv_done, (nkv - 1) & 1);
-    tc_fence_after();
-    const uint32_t qi = qblk * ATT_BM + r;
-    const bool valid = qi < (uint32_t)seq_len;
-    const float inv_l = 1.f / l_run;
-    const int64_t t = (int64_t)seq_start + qi;
-    __nv_bfloat16* orow = O + t * ldo + head * ATT_HD;
+    if (my_blocks > 0) {
+      mbar_wait(&pv_done[t], (my_blocks - 1) & 1);
+      tc_fence_after();
+      const uint32_t qi = q0 + t * 128 + r;
+      const bool valid = qi < (uint32_t)seq_len;
+      const float inv_l = 1.f / l_run;
+      const int64_t tok = (int64_t)seq_start + qi;
+      __nv_bfloat16* orow = O + tok * ldo + head * 128;
 #pragma unroll 1
-    for (uint32_t c = 0; c < 128; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_O + lane_off + c, v);
-      tmem_ld_wait();
-      if (valid) {
+      for (uint32_t c = 0; c < 128; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_O + lane_off + c, v);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (uint32_t i = 0; i < 32; i += 8) {
-          uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
-          o.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
-          o.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
-          o.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
-          *reinterpret_cast<uint4*>(orow + c + i) = o;
+          for (uint32_t i = 0; i < 32; i += 8) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+            o.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
+            o.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
+            o.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
+            *reinterpret_cast<uint4*>(orow + c + i) = o;
+          }
         }
       }
+      if (valid && lse) lse[(int64_t)head * T + tok] = m_run * scale + __logf(l_run);
     }
-    if (valid && lse) lse[(int64_t)head * T + t] = m_run * scale + __logf(l_run);
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 256); }
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace nv
 
 // q, k, v: bf16 row-major [T, *] views with leading dimensions ldq/ldk/ldv (elements); head h occupies
 // columns [h*128, (h+1)*128).  o: [T, H*128] bf16 (ldo).  lse: [H, T] fp32 or null.
-// cu_seqlens: device int32 [B+1]; total_qblocks = sum_b ceil(len_b / 128) (the host knows the lengths).
+// cu_seqlens: device int32 [B+1]; total_qblocks = sum_b ceil(len_b / 128) (the host knows the lengths);
+// the kernel itself works on 256-row blocks: the grid is sized from an upper bound and surplus CTAs exit.
 extern "C" int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
                            int64_t ldo, float* lse, const int* cu_seqlens, int B, int T, int H, int head_dim,
                            int total_qblocks, float scale, void* stream) {
@@ -280,7 +309,9 @@ extern "C" int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
     NV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::DYN_BYTES));
     attr_set = true;
   }
-  dim3 grid(total_qblocks, H);
+  // sum_b ceil(len_b/256) <= ceil((total_qblocks + B) / 2): launch that many, CTAs beyond the real count return
+  const int grid_x = (total_qblocks + B + 1) / 2;
+  dim3 grid(grid_x, H);
   attn_fwd_kernel<<<grid, ATT_THREADS, AttnFwdSmem::DYN_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
       tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(o), ldo, lse, cu_seqlens, B, T, scale);
   NV_LAUNCH_CHECK();
