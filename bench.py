@@ -284,7 +284,7 @@ def main():
     tokens_real = int(text["attention_mask"].sum())
 
     def step_resident():
-        model.zero_grad(set_to_none=False)
+        model.zero_grad(lazy=True)
         loss = nav_step(model, resident, meta, dev, text=text)
         loss.backward()
         if world > 1:
@@ -292,7 +292,7 @@ def main():
         return loss
 
     def step_e2e():
-        model.zero_grad(set_to_none=False)
+        model.zero_grad(lazy=True)
         d = upload()
         loss = nav_step(model, d, meta, dev)          # tokenises the prompt strings on the host, like the reference
         loss.backward()
@@ -354,7 +354,8 @@ def main():
             "config": {"workload": "C2 R2R-shaped training step (panorama+navigation fwd+bwd), B=16/GPU, 36x1408 views, hist=8, "
                                    "24 graph nodes, 15 candidates, seq U{256..1024} (packed: pad tokens not computed), Vicuna-7B random init",
                        "layers": a.layers, "real_tokens_per_step": tokens_real, "l2": "inputs_exceed_l2 (13.5 GB of weights streamed per pass)",
-                       "grad_allreduce": "every step" if world > 1 else "n/a", "optimizer_step": "outside the boundary (train.py:86-89), not timed"},
+                       "grad_allreduce": "every step, layer slices overlapped with the backward" if world > 1 else "n/a",
+                       "zero_grad": "lazy (first wgrad of a step overwrites: beta=0)", "optimizer_step": "outside the boundary (train.py:86-89), not timed"},
             "e2e": {"value": e2e, "unit": "nav-steps/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(launches),

@@ -158,54 +158,51 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);
       constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 128, 1, 1);
       constexpr uint32_t idesc_km = umma_idesc_bf16(128, 128, 0, 1);
+      // loop-invariant operand descriptors (the issuing thread is the serial resource: keep its loop short)
+      uint64_t q_k[2], k_k[2], o_k[2], v_k[2], ds_k[2];
+#pragma unroll
+      for (uint32_t ka = 0; ka < 2; ++ka) {
+        q_k[ka] = umma_smem_desc_sw128(smem_u32(sQ + ka * AB_ATOM), 0, 1024);     // K-major over hd
+        k_k[ka] = umma_smem_desc_sw128(smem_u32(sK + ka * AB_ATOM), 0, 1024);
+        o_k[ka] = umma_smem_desc_sw128(smem_u32(sdO + ka * AB_ATOM), 0, 1024);
+        v_k[ka] = umma_smem_desc_sw128(smem_u32(sV + ka * AB_ATOM), 0, 1024);
+        ds_k[ka] = umma_smem_desc_sw128(smem_u32(sDS + ka * AB_ATOM), 0, 1024);   // K-major over keys
+      }
+      // MN-major views (rows = contraction index, 64-wide MN atoms AB_ATOM bytes apart); k-step = 16 rows = 2048 B
+      const uint64_t p_m = umma_smem_desc_sw128(smem_u32(sP), AB_ATOM, 1024);
+      const uint64_t ds_m = umma_smem_desc_sw128(smem_u32(sDS), AB_ATOM, 1024);
+      const uint64_t o_m = umma_smem_desc_sw128(smem_u32(sdO), AB_ATOM, 1024);
+      const uint64_t q_m = umma_smem_desc_sw128(smem_u32(sQ), AB_ATOM, 1024);
+      const uint64_t k_m = umma_smem_desc_sw128(smem_u32(sK), AB_ATOM, 1024);
       mbar_wait(res_full, 0);
       for (uint32_t n = 0; n < n_it; ++n) {
         mbar_wait(ld_full, n & 1);
         tc_fence_after();
         // S = Q K^T ; dP = dO V^T   (both operands K-major over hd: 2 atoms x 4 k-steps)
 #pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t qd = umma_smem_desc_sw128(smem_u32(sQ + ka * AB_ATOM), 0, 1024);
-          const uint64_t kd = umma_smem_desc_sw128(smem_u32(sK + ka * AB_ATOM), 0, 1024);
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_S, qd + ks * 2, kd + ks * 2, idesc_kk, (ka | ks) ? 1u : 0u);
-        }
+          for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_S, q_k[ka] + ks * 2, k_k[ka] + ks * 2, idesc_kk, (ka | ks) ? 1u : 0u);
 #pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t od = umma_smem_desc_sw128(smem_u32(sdO + ka * AB_ATOM), 0, 1024);
-          const uint64_t vd = umma_smem_desc_sw128(smem_u32(sV + ka * AB_ATOM), 0, 1024);
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dP, od + ks * 2, vd + ks * 2, idesc_kk, (ka | ks) ? 1u : 0u);
-        }
+          for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dP, o_k[ka] + ks * 2, v_k[ka] + ks * 2, idesc_kk, (ka | ks) ? 1u : 0u);
         umma_commit(sdp_full);
         mbar_wait(pds_ready, n & 1);
         tc_fence_after();
         if (MODE == MODE_DKDV) {
-          // dV += P^T dO ; dK += dS^T Q : contraction over the 128 query rows (8 k-steps of 16 rows);
-          // all four operands are MN-major: rows = K index, 64-wide MN atoms AB_ATOM bytes apart.
+          // dV += P^T dO ; dK += dS^T Q : contraction over the 128 query rows (8 k-steps of 16 rows)
 #pragma unroll
-          for (uint32_t ks = 0; ks < 8; ++ks) {
-            const uint64_t pd = umma_smem_desc_sw128(smem_u32(sP + ks * 2048), AB_ATOM, 1024);
-            const uint64_t od = umma_smem_desc_sw128(smem_u32(sdO + ks * 2048), AB_ATOM, 1024);
-            umma_f16_ss(tmem_A0, pd, od, idesc_mm, (n | ks) ? 1u : 0u);
-          }
+          for (uint32_t ks = 0; ks < 8; ++ks) umma_f16_ss(tmem_A0, p_m + ks * 128, o_m + ks * 128, idesc_mm, (n | ks) ? 1u : 0u);
 #pragma unroll
-          for (uint32_t ks = 0; ks < 8; ++ks) {
-            const uint64_t dd = umma_smem_desc_sw128(smem_u32(sDS + ks * 2048), AB_ATOM, 1024);
-            const uint64_t qd = umma_smem_desc_sw128(smem_u32(sQ + ks * 2048), AB_ATOM, 1024);
-            umma_f16_ss(tmem_A1, dd, qd, idesc_mm, (n | ks) ? 1u : 0u);
-          }
+          for (uint32_t ks = 0; ks < 8; ++ks) umma_f16_ss(tmem_A1, ds_m + ks * 128, q_m + ks * 128, idesc_mm, (n | ks) ? 1u : 0u);
         } else {
           // dQ += dS K : A = dS K-major over keys (2 atoms x 4 k-steps), B = K MN-major (hd contiguous)
 #pragma unroll
-          for (uint32_t ka = 0; ka < 2; ++ka) {
+          for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
-            for (uint32_t ks = 0; ks < 4; ++ks) {
-              const uint64_t dd = umma_smem_desc_sw128(smem_u32(sDS + ka * AB_ATOM), 0, 1024) + ks * 2;
-              const uint64_t kd = umma_smem_desc_sw128(smem_u32(sK + (ka * 64 + ks * 16) * 128), AB_ATOM, 1024);
-              umma_f16_ss(tmem_A0, dd, kd, idesc_km, (n | ka | ks) ? 1u : 0u);
-            }
-          }
+            for (uint32_t ks = 0; ks < 4; ++ks)
+              umma_f16_ss(tmem_A0, ds_k[ka] + ks * 2, k_m + ((ka * 64 + ks * 16) * 128 >> 4), idesc_km, (n | ka | ks) ? 1u : 0u);
         }
         umma_commit(acc_done);
       }

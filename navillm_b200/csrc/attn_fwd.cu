@@ -131,29 +131,38 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // P (K-major) x V (MN-major: hd contiguous)
-      auto issue_s = [&](uint32_t t) {
+      // All operand descriptors are loop-invariant: build them once so that the single issuing thread spends
+      // its cycles on tcgen05.mma, not on descriptor arithmetic (it is the serial bottleneck otherwise).
+      uint64_t qd[2][2], pd[2][2], kd[2], vd[2];
+#pragma unroll
+      for (uint32_t t = 0; t < 2; ++t)
 #pragma unroll
         for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t ad = umma_smem_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024);
-          const uint64_t bd = umma_smem_desc_sw128(smem_u32(sK + ka * ATT_ATOM_BYTES), 0, 1024);
+          qd[t][ka] = umma_smem_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024);
+          pd[t][ka] = umma_smem_desc_sw128(smem_u32(sP + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024);
+        }
+#pragma unroll
+      for (uint32_t ka = 0; ka < 2; ++ka) kd[ka] = umma_smem_desc_sw128(smem_u32(sK + ka * ATT_ATOM_BYTES), 0, 1024);
+      // V tile: rows = keys (K dim), 128 B of hd per row per atom; atoms (hd halves) ATT_ATOM_BYTES apart
+#pragma unroll
+      for (uint32_t st = 0; st < 2; ++st) vd[st] = umma_smem_desc_sw128(smem_u32(sV + st * ATT_TILE_BYTES), ATT_ATOM_BYTES, 1024);
+      auto issue_s = [&](uint32_t t) {
+        const uint32_t d_tmem = tmem_base + t * 128;
+#pragma unroll
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_base + t * 128, ad + ks * 2, bd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
-        }
+            umma_f16_ss(d_tmem, qd[t][ka] + ks * 2, kd[ka] + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
         umma_commit(&s_full[t]);
       };
       auto issue_pv = [&](uint32_t t, uint32_t st, bool accumulate) {
+        const uint32_t d_tmem = tmem_base + 256 + t * 128;
 #pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) {
-            const uint64_t ad = umma_smem_desc_sw128(smem_u32(sP + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024) + ks * 2;
-            // V tile: rows = keys (K dim), 128 B of hd per row per atom; atoms (hd halves) ATT_ATOM_BYTES apart
-            const uint64_t bd = umma_smem_desc_sw128(
-                smem_u32(sV + st * ATT_TILE_BYTES + (ka * 64 + ks * 16) * 128), ATT_ATOM_BYTES, 1024);
-            umma_f16_ss(tmem_base + 256 + t * 128, ad, bd, idesc_pv, (accumulate || (ka | ks)) ? 1u : 0u);
-          }
-        }
+          for (uint32_t ks = 0; ks < 4; ++ks)   // key rows ka*64 + ks*16 -> byte offset * 128 >> 4
+            umma_f16_ss(d_tmem, pd[t][ka] + ks * 2, vd[st] + ((ka * 64 + ks * 16) * 128 >> 4), idesc_pv,
+                        (accumulate || (ka | ks)) ? 1u : 0u);
         umma_commit(&pv_done[t]);
       };
       mbar_wait(q_full, 0);

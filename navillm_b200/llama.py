@@ -143,6 +143,9 @@ class FlatParams:
         return self.params[0].data_ptr() == self._ptr0 and self.params[0].grad is not None and \
             self.params[0].grad.data_ptr() == self.flat_grad.data_ptr()
 
+    def offset_of(self, p: nn.Parameter) -> int:
+        return self.offsets[next(k for k, q in enumerate(self.params) if q is p)]
+
     def reattach_grads(self) -> None:
         """After ``optimizer.zero_grad(set_to_none=True)``: zero the buffer and hand the views back."""
         self.flat_grad.zero_()
@@ -251,40 +254,51 @@ class LlamaCore:
         return x, ((saved, (pos, cu, list(seqlens))) if save else None)
 
     # -------------------------------------------------------------------------------------------------
-    def backward(self, dx: torch.Tensor, tape) -> torch.Tensor:
+    def backward(self, dx: torch.Tensor, tape, layer_done=None) -> torch.Tensor:
         """dx: [T, D] bf16 gradient w.r.t. the forward's hidden output; ``tape`` from that forward (consumed).
-        Accumulates every weight gradient in place and returns the gradient w.r.t. the input embeddings."""
+        Accumulates every weight gradient in place (or OVERWRITES it when ``flat.overwrite_layer_grads`` is set
+        by a lazy zero_grad: beta = 0 instead of zero-fill + read-modify-write) and returns the gradient w.r.t.
+        the input embeddings.  ``layer_done(l)`` is called after layer l's gradients have been enqueued (used to
+        overlap the data-parallel all-reduce with the rest of the backward)."""
         if tape is None:
             raise RuntimeError("LlamaCore.backward: the forward ran without saving activations (no_grad / eval-only)")
         saved, (pos, cu, seqlens) = tape
         d = self.d
         H = d.n_heads
+        acc = not getattr(self.flat, "overwrite_layer_grads", False)
+
+        def add(g):
+            return g if acc else None
+
         for l in range(d.n_layers - 1, -1, -1):
             lyr, s = self.model.layers[l], saved[l]
             # ---- MLP:  x_out = xm + down(swiglu(gate_up(rmsnorm2(xm)))) ----
             dh = ops.gemm(dx, self.wd[l], b_mn=True)                                   # [T,F]  dgrad
-            ops.gemm(dx, s.h, a_mn=True, b_mn=True, out=self.gd[l], addend=self.gd[l])  # dWd += dx^T h
+            ops.gemm(dx, s.h, a_mn=True, b_mn=True, out=self.gd[l], addend=add(self.gd[l]))  # dWd += dx^T h
             dgu = ops.swiglu_bwd(s.gu, dh)
             del dh
             dxn2 = ops.gemm(dgu, self.wgu[l], b_mn=True)                               # [T,D]
-            ops.gemm(dgu, s.xn2, a_mn=True, b_mn=True, out=self.ggu[l], addend=self.ggu[l])
+            ops.gemm(dgu, s.xn2, a_mn=True, b_mn=True, out=self.ggu[l], addend=add(self.ggu[l]))
             del dgu
             dxm = ops.rmsnorm_bwd(s.xm, lyr.post_attention_layernorm.weight.data, s.rstd2, dxn2, dres=dx,
-                                  dw=lyr.post_attention_layernorm.weight.grad)
+                                  dw=lyr.post_attention_layernorm.weight.grad, accumulate_dw=acc)
             del dxn2
             # ---- attention:  xm = x + o_proj(attn(rope(qkv(rmsnorm1(x))))) ----
             dao = ops.gemm(dxm, self.wo[l], b_mn=True)
-            ops.gemm(dxm, s.ao, a_mn=True, b_mn=True, out=self.go[l], addend=self.go[l])
+            ops.gemm(dxm, s.ao, a_mn=True, b_mn=True, out=self.go[l], addend=add(self.go[l]))
             dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H)
             del dao
             ops.rope_(dqkv, pos, self.cos, self.sin, 2 * H, d.head_dim, backward=True)
             dxn = ops.gemm(dqkv, self.wqkv[l], b_mn=True)
-            ops.gemm(dqkv, s.xn, a_mn=True, b_mn=True, out=self.gqkv[l], addend=self.gqkv[l])
+            ops.gemm(dqkv, s.xn, a_mn=True, b_mn=True, out=self.gqkv[l], addend=add(self.gqkv[l]))
             del dqkv
             dx = ops.rmsnorm_bwd(s.x, lyr.input_layernorm.weight.data, s.rstd1, dxn, dres=dxm,
-                                 dw=lyr.input_layernorm.weight.grad)
+                                 dw=lyr.input_layernorm.weight.grad, accumulate_dw=acc)
             del dxn, dxm
             saved[l] = None
+            if layer_done is not None:
+                layer_done(l)
+        self.flat.overwrite_layer_grads = False
         return dx
 
 

@@ -146,7 +146,7 @@ class _LMFn(torch.autograd.Function):
         dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)
         dhid = torch.zeros(shape, dtype=bf16, device=dg.device)
         ops.scatter_rows_(dg, rows, dhid)
-        dx = core.backward(dhid, ctx.tape)
+        dx = core.backward(dhid, ctx.tape, layer_done=lm._grad_sync_hook())
         ops.embed_bwd_weight_(dx, pp.ids, lm.model.embed_tokens.weight.grad)
         dvis = ops.embed_bwd_vis(dx, pp.vis_src, ctx.n_vis) if ctx.has_vis else None
         ctx.saved = ctx.tape = None
@@ -242,6 +242,60 @@ class ModifiedLlamaForCausalLM(nn.Module):
 
     def _device(self) -> torch.device:
         return self.model.norm.weight.device
+
+    # ---- data-parallel gradient exchange overlapped with the backward ----
+    sync_grads = True            # False inside NavModel.no_sync()
+    overlap_grad_reduce = True
+    reduce_chunk_layers = 4
+
+    def _grad_sync_hook(self):
+        """Returns a per-layer callback for LlamaCore.backward that all-reduces (AVG) the flat-gradient slice of
+        every finished group of ``reduce_chunk_layers`` layers asynchronously: NCCL waits only for the kernels
+        enqueued so far and runs while the remaining layers' backward GEMMs execute.  None when not applicable."""
+        import torch.distributed as dist
+        if not (self.sync_grads and self.overlap_grad_reduce and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size() > 1):
+            return None
+        flat, layers, n = self.flat, self.model.layers, self.dims.n_layers
+        starts = [flat.offset_of(l.self_attn.q_proj.weight) for l in layers] + [flat.offset_of(self.model.embed_tokens.weight)]
+        chunk = max(1, self.reduce_chunk_layers)
+        self._pending_reduces = []
+        self._layers_reduced = True
+        avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+        ws = dist.get_world_size()
+
+        def done(l):
+            if l % chunk != 0:
+                return
+            hi = min(l + chunk, n)
+            sl = flat.flat_grad[starts[l]:starts[hi]]
+            h = dist.all_reduce(sl, op=avg, async_op=True)
+            self._pending_reduces.append((h, sl if avg == dist.ReduceOp.SUM else None, ws))
+        return done
+
+    def finish_grad_sync(self) -> int:
+        """Wait for the overlapped layer reductions and reduce what they did not cover (embeddings, final norm,
+        lm_head, heads).  Returns the number of collectives issued here."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return 0
+        ws = dist.get_world_size()
+        avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
+        pend = getattr(self, "_pending_reduces", [])
+        for h, sl, _ in pend:
+            h.wait()
+            if sl is not None:
+                sl.div_(ws)
+        self._pending_reduces = []
+        if getattr(self, "_layers_reduced", False):
+            tail = self.flat.flat_grad[self.flat.offset_of(self.model.embed_tokens.weight):]
+            self._layers_reduced = False
+        else:
+            tail = self.flat.flat_grad
+        dist.all_reduce(tail, op=avg)
+        if avg == dist.ReduceOp.SUM:
+            tail.div_(ws)
+        return 1
 
     def _ensure(self):
         dev = self._device()

@@ -242,17 +242,34 @@ class NavModel(nn.Module):
         """DDP-compatible context (tasks/agents/mp3d_agent.py:661-667): gradients accumulate locally; the
         all-reduce is issued by ``allreduce_grads`` on the first backward outside this context."""
         old = self._sync_grads
-        self._sync_grads = False
+        self._sync_grads = self.lang_model.sync_grads = False
         try:
             yield
         finally:
-            self._sync_grads = old
+            self._sync_grads = self.lang_model.sync_grads = old
 
     def allreduce_grads(self, average: bool = True):
         """ONE NCCL all-reduce per dtype over the flat gradient buffers (replaces DDP's
         bucketed reduction of tools/optims.py:52-54).  No-op without an initialised process group."""
         from .llama import allreduce_flat_grads
-        return allreduce_flat_grads([self.lang_model.flat, self._flat32], average=average)
+        n = self.lang_model.finish_grad_sync()           # LM buffer: layer slices were reduced during the backward
+        return n + allreduce_flat_grads([self._flat32], average=average)
+
+    def zero_grad(self, set_to_none: bool = False, lazy: bool = False):
+        """Gradients live in two flat buffers, so zeroing is two fills instead of one per parameter.  With
+        ``lazy=True`` the per-layer LM gradients are not zeroed at all: the next backward OVERWRITES them
+        (beta = 0 wgrad epilogue) -- identical result, 27 GB less HBM traffic per step; until that backward runs
+        their ``.grad`` views hold stale values."""
+        if self.lang_model.core is None or self._flat32 is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        self._ensure()
+        lm = self.lang_model
+        self._flat32.flat_grad.zero_()
+        if lazy:
+            lm.flat.flat_grad[lm.flat.offset_of(lm.model.embed_tokens.weight):].zero_()
+            lm.flat.overwrite_layer_grads = True
+        else:
+            lm.flat.flat_grad.zero_()
 
     def _anchor_t(self):
         return self._anchor.detach().requires_grad_(torch.is_grad_enabled())
