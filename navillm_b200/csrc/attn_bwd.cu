@@ -22,7 +22,7 @@ namespace nv {
 
 constexpr uint32_t AB_TILE = 128 * 128 * 2;
 constexpr uint32_t AB_ATOM = 128 * 128;
-constexpr uint32_t AB_THREADS = 192;
+constexpr uint32_t AB_THREADS = 320;  // TMA warp, MMA warp, 8 compute warps (2 per TMEM lane quarter: column halves)
 constexpr int MODE_DKDV = 0, MODE_DQ = 1;
 
 struct AttnBwdSmem {
@@ -114,7 +114,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     mbar_init(res_full, 1);
     mbar_init(ld_full, 1);
     mbar_init(sdp_full, 1);
-    mbar_init(pds_ready, 128);
+    mbar_init(pds_ready, 256);
     mbar_init(acc_done, 1);
     fence_mbar_init();
   }
@@ -208,9 +208,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       }
     }
   } else {
+    // Two warps share each TMEM lane quarter (a warp may touch lanes 32*(warp%4)..+31 only) and split the 128
+    // key columns in halves: no row reductions are needed in the backward (LSE and D are precomputed), so the
+    // element-wise phase parallelises over columns and every SMSP holds two compute warps to hide latencies.
     const uint32_t quarter = warp & 3;
     const uint32_t r = quarter * 32 + lane;
     const uint32_t lane_off = (quarter * 32) << 16;
+    const uint32_t c_begin = ((warp - 2) >> 2) * 64, c_end = c_begin + 64;
     const float sl2 = scale * 1.4426950408889634f;
     for (uint32_t n = 0; n < n_it; ++n) {
       const uint32_t qb = (MODE == MODE_DKDV) ? (it_begin + n) : own;  // query block of this iteration
@@ -224,7 +228,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (uint32_t c = 0; c < 128; c += 32) {
+      for (uint32_t c = c_begin; c < c_end; c += 32) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32(tmem_S + lane_off + c, sv);
         tmem_ld_32x32b_x32(tmem_dP + lane_off + c, dv);
@@ -270,7 +274,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       if (MODE == MODE_DKDV) dst = (which == 0) ? (out1 + t * ld1 + head * 128) : (out0 + t * ld0 + head * 128);
       else dst = out0 + t * ld0 + head * 128;
 #pragma unroll 1
-      for (uint32_t c = 0; c < 128; c += 32) {
+      for (uint32_t c = c_begin; c < c_end; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tm + lane_off + c, v);
         tmem_ld_wait();
