@@ -44,6 +44,24 @@ B_STEP, N_VIEWS, N_HIST, N_GMAP, N_CAND = 16, 36, 8, 24, 16
 LEN_LO, LEN_HI = 256, 1024
 
 
+def gemm_traffic():
+    """Average DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/r01_gemm_ncu_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of GEMM launches inside a step)."""
+    p = ROOT / "profiles" / "r01_gemm_ncu_summary.json"
+    if not p.exists():
+        return None, None
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    tot, n = 0.0, 0
+    for k in json.loads(p.read_text())["kernels"]:
+        b = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = k[key].split()
+            b += float(v) * unit[u]
+        tot += b
+        n += 1
+    return (tot / n if n else None), f"mean over {n} captured launches, {p.name}"
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -361,7 +379,9 @@ def main():
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / pk["bf16_tflops"]) if achieved else None, "peak_src": pk["src"] + " (sustained cuBLAS bf16)",
-                         "launches_per_step": n_gemm // max(a.steps, 1), "share_of_step": gemm_ms / ms, "traffic": None,
+                         "launches_per_step": n_gemm // max(a.steps, 1), "share_of_step": gemm_ms / ms,
+                         "traffic": gemm_traffic()[0], "traffic_unit": "bytes/launch (DRAM read+write)", "traffic_src": gemm_traffic()[1],
+                         "algorithmic_bytes_per_launch_mean": None,
                          "step_algorithmic_tflop": algo_step / 1e12,
                          "step_frac_of_peak": algo_step / 1e12 / (ms / a.steps / 1e3) / pk["bf16_tflops"]},
             "clocks": clk.summary(),

@@ -284,7 +284,9 @@ extern "C" int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   NV_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0, "nv_gemm_bf16: lda/ldb must be multiples of 8 (got %lld, %lld)",
              (long long)lda, (long long)ldb);
   if (block_n == 0) block_n = (N >= 2048) ? 256 : 128;
-  NV_REQUIRE(block_n == 128 || block_n == 256, "nv_gemm_bf16: block_n must be 128 or 256");
+  if (block_n == 512)   // CTA-pair kernel (cta_group::2), 256 x 256 tile per SM pair
+    return gemm_bf16_2cta_dispatch(A, lda, a_mn, B, ldb, b_mn, C, ldc, addend, ld_add, M, N, K, flags, stream);
+  NV_REQUIRE(block_n == 128 || block_n == 256, "nv_gemm_bf16: block_n must be 128, 256 or 512 (2-CTA)");
 
   CUtensorMap ta, tb;
   int rc;

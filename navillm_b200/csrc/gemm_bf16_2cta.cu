@@ -1,0 +1,324 @@
+// navillm_b200 — bf16 GEMM on tcgen05 with CTA pairs (cta_group::2): 256 x 256 output tile per SM pair.
+//
+// Same contract as gemm_bf16.cu (C[M,N] = A·B (+addend), K-/MN-major operands), different mapping:
+// two CTAs of a cluster (adjacent SMs) cooperate on one UMMA_M = 256 instruction stream issued by the
+// leader CTA.  Each CTA stages its own 128 rows of A and HALF of the B tile (128 of the 256 N rows); the
+// tensor cores of the pair read both halves of B across the pair, so per-SM shared-memory traffic and
+// capacity for B halve (32 KB per stage instead of 48 KB -> 6 stages, and less energy per FLOP on a
+// power-capped part).  Accumulators: each CTA's TMEM holds its own 128 rows x 256 columns, 2 stages.
+//
+//   warp 0 (1 lane, both CTAs)  TMA producer; completes transactions on the LEADER's full barrier
+//   warp 1 (1 lane, leader)     tcgen05.mma.cta_group::2 issuer; commits are multicast to both CTAs
+//   warps 2..5 (both CTAs)      epilogue for the CTA's own 128 rows; arrive on the leader's tmem_empty
+#include "nv_common.cuh"
+#include "nv_host.h"
+
+namespace nv {
+
+constexpr uint32_t G2_BM = 128;       // rows per CTA (256 per pair)
+constexpr uint32_t G2_BN = 256;       // columns per pair
+constexpr uint32_t G2_BNH = 128;      // B rows staged per CTA
+constexpr uint32_t G2_BK = 64;
+constexpr uint32_t G2_STAGES = 6;
+constexpr uint32_t G2_THREADS = 192;
+constexpr uint32_t G2_GROUP_M = 8;    // pair-tiles (256 rows) per rasterisation group
+constexpr uint32_t G2_A_BYTES = G2_BM * G2_BK * 2;
+constexpr uint32_t G2_B_BYTES = G2_BNH * G2_BK * 2;
+constexpr uint32_t G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
+constexpr uint32_t G2_BAR_OFF = G2_STAGES * G2_STAGE_BYTES;
+constexpr uint32_t G2_NUM_BARS = 2 * G2_STAGES + 4;
+constexpr uint32_t G2_DYN_BYTES = G2_BAR_OFF + G2_NUM_BARS * 8 + 16 + 1024;
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose transaction bytes complete on the LEADER CTA's mbarrier (same smem offset, rank bit cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int32_t c0,
+                                                int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// commit: arrive (once the issued MMAs are done) on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+      ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void tile_coords2(uint32_t tile, uint32_t num_m, uint32_t num_n, uint32_t& m_blk,
+                                             uint32_t& n_blk) {
+  const uint32_t group_size = G2_GROUP_M * num_n;
+  const uint32_t g = tile / group_size;
+  const uint32_t first_m = g * G2_GROUP_M;
+  const uint32_t gm = min(num_m - first_m, G2_GROUP_M);
+  const uint32_t r = tile - g * group_size;
+  m_blk = first_m + r % gm;
+  n_blk = r / gm;
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                       void* __restrict__ Cout, int64_t ldc, const __nv_bfloat16* __restrict__ addend, int64_t ld_add,
+                       uint32_t M, uint32_t N, uint32_t K, uint32_t flags) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + G2_STAGES * G2_A_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFF);
+  uint64_t* full_bar = bars;                       // used in the leader
+  uint64_t* empty_bar = bars + G2_STAGES;          // per CTA
+  uint64_t* tmem_full = bars + 2 * G2_STAGES;      // per CTA [2]
+  uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2; // used in the leader [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + G2_NUM_BARS);
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+    for (uint32_t i = 0; i < G2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);   // leader's arrive.expect_tx + the peer's remote arrive
+      mbar_init(&empty_bar[i], 1);  // multicast commit from the leader
+    }
+    for (uint32_t i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);   // multicast commit
+      mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps of each CTA
+    }
+    fence_mbar_init();
+  }
+  cluster_sync_all();                 // barrier inits of both CTAs visible before any remote arrive / TMA
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr_smem, 512);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const uint32_t num_m = ceil_div_u32(M, 2 * G2_BM);
+  const uint32_t num_n = ceil_div_u32(N, G2_BN);
+  const uint32_t num_tiles = num_m * num_n;
+  const uint32_t num_kb = ceil_div_u32(K, G2_BK);
+  const uint32_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        uint32_t m_blk, n_blk;
+        tile_coords2(tile, num_m, num_n, m_blk, n_blk);
+        const int32_t m0 = m_blk * 2 * G2_BM + rank * G2_BM;    // this CTA's A rows
+        const int32_t n0 = n_blk * G2_BN + rank * G2_BNH;       // this CTA's half of the B tile
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          else mbar_arrive_remote(&full_bar[stage], 0);
+          const int32_t k0 = kb * G2_BK;
+          uint8_t* sa = smem_a + stage * G2_A_BYTES;
+          uint8_t* sb = smem_b + stage * G2_B_BYTES;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(sa, &tmap_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (uint32_t i = 0; i < G2_BM / 64; ++i)
+              tma_load_2d_2sm(sa + i * (G2_BK * 128), &tmap_a, &full_bar[stage], m0 + i * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(sb, &tmap_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (uint32_t i = 0; i < G2_BNH / 64; ++i)
+              tma_load_2d_2sm(sb + i * (G2_BK * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
+          }
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader only) =====================
+    if (leader && lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 0, B_LBO = B_MN ? G2_BK * 128 : 0;
+      constexpr uint32_t A_KADV = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      constexpr uint32_t B_KADV = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
+      uint32_t stage = 0, phase = 0, iter = 0;
+      for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+        const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * G2_BN;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * G2_A_BYTES), A_LBO, 1024);
+          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * G2_B_BYTES), B_LBO, 1024);
+#pragma unroll
+          for (uint32_t k = 0; k < G2_BK / 16; ++k)
+            umma_f16_ss_2sm(tmem_d, adesc + k * A_KADV, bdesc + k * B_KADV, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage]);
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full[acc]);
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5, both CTAs: own 128 rows) =====================
+    const uint32_t quarter = warp & 3;
+    const bool do_add = (flags & 1u) != 0;
+    const bool out_f32 = (flags & 2u) != 0;
+    uint32_t iter = 0;
+    for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      uint32_t m_blk, n_blk;
+      tile_coords2(tile, num_m, num_n, m_blk, n_blk);
+      const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t row = m_blk * 2 * G2_BM + rank * G2_BM + quarter * 32 + lane;
+      const uint32_t col0 = n_blk * G2_BN;
+      const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * G2_BN;
+#pragma unroll 1
+      for (uint32_t c = 0; c < G2_BN; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c, v);
+        tmem_ld_wait();
+        const uint32_t col = col0 + c;
+        if (row < M && col < N) {
+          if (out_f32) {
+            float* dst = reinterpret_cast<float*>(Cout) + static_cast<int64_t>(row) * ldc + col;
+            if (col + 32 <= N && (ldc & 3) == 0) {
+#pragma unroll
+              for (uint32_t j = 0; j < 32; j += 4)
+                *reinterpret_cast<uint4*>(dst + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+              for (uint32_t j = 0; j < 32; ++j)
+                if (col + j < N) dst[j] = __uint_as_float(v[j]);
+            }
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<int64_t>(row) * ldc + col;
+            const __nv_bfloat16* add = do_add ? addend + static_cast<int64_t>(row) * ld_add + col : nullptr;
+            if (col + 32 <= N && (ldc & 7) == 0 && (!do_add || (ld_add & 7) == 0)) {
+#pragma unroll
+              for (uint32_t j = 0; j < 32; j += 8) {
+                uint4 o;
+                o.x = pack_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+                o.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                o.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+                o.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+                if (do_add) {
+                  const uint4 a = *reinterpret_cast<const uint4*>(add + j);
+                  o.x = pack_bf16x2(bf16_lo(o.x) + bf16_lo(a.x), bf16_hi(o.x) + bf16_hi(a.x));
+                  o.y = pack_bf16x2(bf16_lo(o.y) + bf16_lo(a.y), bf16_hi(o.y) + bf16_hi(a.y));
+                  o.z = pack_bf16x2(bf16_lo(o.z) + bf16_lo(a.z), bf16_hi(o.z) + bf16_hi(a.z));
+                  o.w = pack_bf16x2(bf16_lo(o.w) + bf16_lo(a.w), bf16_hi(o.w) + bf16_hi(a.w));
+                }
+                *reinterpret_cast<uint4*>(dst + j) = o;
+              }
+            } else {
+#pragma unroll
+              for (uint32_t j = 0; j < 32; ++j) {
+                if (col + j < N) {
+                  float x = bf16_round(__uint_as_float(v[j]));
+                  if (do_add) x = x + __bfloat162float(add[j]);
+                  dst[j] = __float2bfloat16_rn(x);
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (leader) mbar_arrive(&tmem_empty[acc]);
+        else mbar_arrive_remote(&tmem_empty[acc], 0);
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // both CTAs done with TMEM and with each other's barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
+  }
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int64_t ldc, const void* addend,
+                            int64_t ld_add, uint32_t M, uint32_t N, uint32_t K, uint32_t flags, cudaStream_t stream) {
+  auto kern = gemm_bf16_tcgen05_2cta<A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
+    attr_set = true;
+  }
+  const uint32_t tiles = ceil_div_u32(M, 2 * G2_BM) * ceil_div_u32(N, G2_BN);
+  uint32_t clusters = min(tiles, (uint32_t)sm_count() / 2);
+  kern<<<clusters * 2, G2_THREADS, G2_DYN_BYTES, stream>>>(ta, tb, C, ldc, reinterpret_cast<const __nv_bfloat16*>(addend),
+                                                            ld_add, M, N, K, flags);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+// Called from nv_gemm_bf16 when block_n == 512 (2-CTA, 256x256 pair tile).
+int gemm_bf16_2cta_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* C,
+                            int64_t ldc, const void* addend, int64_t ld_add, int M, int N, int K, unsigned flags,
+                            cudaStream_t stream) {
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn) rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, G2_BM);
+  else       rc = make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, G2_BK);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, G2_BNH);
+  else       rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, G2_BK);
+  if (rc) return rc;
+  if (!a_mn && !b_mn) return launch_gemm_2cta<false, false>(ta, tb, C, ldc, addend, ld_add, M, N, K, flags, stream);
+  if (!a_mn && b_mn) return launch_gemm_2cta<false, true>(ta, tb, C, ldc, addend, ld_add, M, N, K, flags, stream);
+  if (a_mn && b_mn) return launch_gemm_2cta<true, true>(ta, tb, C, ldc, addend, ld_add, M, N, K, flags, stream);
+  return launch_gemm_2cta<true, false>(ta, tb, C, ldc, addend, ld_add, M, N, K, flags, stream);
+}
+
+}  // namespace nv

@@ -43,4 +43,9 @@ int sm_count();
 int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
                  uint64_t outer_stride_bytes, uint32_t box_inner, uint32_t box_outer);
 
+// gemm_bf16_2cta.cu: cta_group::2 variant (256x256 tile per SM pair), selected with block_n == 512
+int gemm_bf16_2cta_dispatch(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* C,
+                            int64_t ldc, const void* addend, int64_t ld_add, int M, int N, int K, unsigned flags,
+                            cudaStream_t stream);
+
 }  // namespace nv

@@ -201,7 +201,7 @@ def rope_tables(d: LlamaDims, device) -> tuple:
 
 
 class _Saved:
-    __slots__ = ("x", "rstd1", "xn", "qkv", "ao", "lse", "xm", "rstd2", "xn2", "gu", "h")
+    __slots__ = ("x", "rstd1", "xn", "qkv", "ao", "lse", "xm", "rstd2", "xn2", "gu", "h", "rows", "ao_r")
 
 
 class LlamaCore:
@@ -227,14 +227,21 @@ class LlamaCore:
         self.cos, self.sin = rope_tables(dims, flat.flat.device)
 
     # -------------------------------------------------------------------------------------------------
-    def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True, kv_sink=None):
+    def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True, kv_sink=None,
+                out_rows: Optional[torch.Tensor] = None):
         """x: [T, D] bf16 input embeddings (packed); pos: int32 [T]; cu: int32 [B+1] (device); seqlens: host
         lengths.  Returns (residual stream after the last layer BEFORE the final RMSNorm, tape) where ``tape``
         holds the per-layer activations for ``backward`` (None when save=False).  The tape travels with the
-        caller (autograd ctx), so several forwards may be in flight before their backwards run."""
+        caller (autograd ctx), so several forwards may be in flight before their backwards run.
+
+        ``out_rows`` (int32 [R], device): only these rows of the output are needed (the <cls_1> rows in the
+        navigation / grounding modes, the label rows in the LM-loss modes, the last rows in prefill).  The last
+        layer then runs o_proj / MLP on R rows instead of T (its K,V still come from all rows) and the return
+        value is [R, D].  The reference computes all positions and reads only these."""
         d = self.d
         H = d.n_heads
         saved: List[_Saved] = []
+        last = d.n_layers - 1
         for l, lyr in enumerate(self.model.layers):
             s = _Saved()
             s.x = x
@@ -244,7 +251,13 @@ class LlamaCore:
             if kv_sink is not None:
                 kv_sink(l, s.qkv)                      # prefill of generate(): post-RoPE K,V go to the cache
             s.ao, s.lse = ops.attn_fwd(s.qkv, cu, seqlens, H)
-            s.xm = ops.gemm(s.ao, self.wo[l], addend=x)
+            s.rows = None
+            ao, xin = s.ao, x
+            if out_rows is not None and l == last:
+                s.rows = out_rows
+                ao = s.ao_r = ops.gather_rows(s.ao, out_rows)
+                xin = ops.gather_rows(x, out_rows)
+            s.xm = ops.gemm(ao, self.wo[l], addend=xin)
             s.xn2, s.rstd2 = ops.rmsnorm_fwd(s.xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
             s.gu = ops.gemm(s.xn2, self.wgu[l])
             s.h = ops.swiglu_fwd(s.gu)
@@ -285,7 +298,17 @@ class LlamaCore:
             del dxn2
             # ---- attention:  xm = x + o_proj(attn(rope(qkv(rmsnorm1(x))))) ----
             dao = ops.gemm(dxm, self.wo[l], b_mn=True)
-            ops.gemm(dxm, s.ao, a_mn=True, b_mn=True, out=self.go[l], addend=add(self.go[l]))
+            if s.rows is None:
+                ops.gemm(dxm, s.ao, a_mn=True, b_mn=True, out=self.go[l], addend=add(self.go[l]))
+            else:
+                # pruned last layer: everything above ran on the R requested rows; scatter back to [T, D]
+                ops.gemm(dxm, s.ao_r, a_mn=True, b_mn=True, out=self.go[l], addend=add(self.go[l]))
+                full = torch.zeros_like(s.ao)
+                ops.scatter_rows_(dao, s.rows, full)
+                dao = full
+                full = torch.zeros_like(s.x)
+                ops.scatter_rows_(dxm, s.rows, full)
+                dxm = full
             dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H)
             del dao
             ops.rope_(dqkv, pos, self.cos, self.sin, 2 * H, d.head_dim, backward=True)

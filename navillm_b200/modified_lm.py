@@ -108,25 +108,24 @@ class _LMFn(torch.autograd.Function):
         core, d = lm.core, lm.dims
         E = lm.model.embed_tokens.weight.data
         x = ops.embed_fwd(pp.ids, E, pp.vis_src if vis is not None else None, vis)
-        hid, ctx.tape = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=train)
+        if mode == "loss":
+            rows = pp.loss_rows
+        # the stack returns only the requested rows (last layer pruned to them)
+        g, ctx.tape = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=train, out_rows=rows)
         ctx.lm, ctx.pp, ctx.mode, ctx.has_vis = lm, pp, mode, vis is not None
         ctx.n_vis = 0 if vis is None else vis.shape[0]
+        hn, rstd = ops.rmsnorm_fwd(g, lm.model.norm.weight.data, d.rms_eps)
         if mode == "rows":
-            g = ops.gather_rows(hid, rows)
-            hn, rstd = ops.rmsnorm_fwd(g, lm.model.norm.weight.data, d.rms_eps)
-            ctx.saved = (g, rstd, rows, hid.shape)
+            ctx.saved = (g, rstd)
             return hn
         # ---- LM loss on the label rows only ----
-        rows = pp.loss_rows
-        g = ops.gather_rows(hid, rows)
-        hn, rstd = ops.rmsnorm_fwd(g, lm.model.norm.weight.data, d.rms_eps)
         V = lm.lm_head.weight.shape[0]
         logits = torch.empty((g.shape[0], (V + 63) // 64 * 64), dtype=bf16, device=g.device)[:, :V]   # 16-byte aligned rows
         ops.gemm(hn, lm.lm_head.weight.data, out=logits)                 # [Nl, V] bf16
         row_loss, dlogits = ops.ce_fwd_bwd(logits, pp.loss_tgt, lm.special_ids_dev,
                                            grad_scale=(1.0 / max(pp.n_loss, 1)) if train else None)
         loss = row_loss.sum() / max(pp.n_loss, 1)
-        ctx.saved = (g, rstd, rows, hid.shape, hn, dlogits)
+        ctx.saved = (g, rstd, hn, dlogits)
         return loss.to(bf16) if lm.model_type == bf16 else loss           # reference: CE on bf16 logits -> bf16 loss
 
     @staticmethod
@@ -135,18 +134,16 @@ class _LMFn(torch.autograd.Function):
         core, d = lm.core, lm.dims
         normw = lm.model.norm.weight
         if ctx.mode == "rows":
-            g, rstd, rows, shape = ctx.saved
+            g, rstd = ctx.saved
             dy = dout.contiguous().to(bf16)
         else:
-            g, rstd, rows, shape, hn, dlogits = ctx.saved
+            g, rstd, hn, dlogits = ctx.saved
             # dlogits was produced with scale 1/N; fold the incoming scalar gradient in on the device (no sync)
             dlogits.copy_(dlogits.float() * dout.float())        # in place: keeps the 16-byte-aligned row stride
             dy = ops.gemm(dlogits, lm.lm_head.weight.data, b_mn=True)                    # [Nl, D]
             ops.gemm(dlogits, hn, a_mn=True, b_mn=True, out=lm.lm_head.weight.grad, addend=lm.lm_head.weight.grad)
-        dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)
-        dhid = torch.zeros(shape, dtype=bf16, device=dg.device)
-        ops.scatter_rows_(dg, rows, dhid)
-        dx = core.backward(dhid, ctx.tape, layer_done=lm._grad_sync_hook())
+        dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)                     # [R, D]: gradient at the requested rows
+        dx = core.backward(dg, ctx.tape, layer_done=lm._grad_sync_hook())
         ops.embed_bwd_weight_(dx, pp.ids, lm.model.embed_tokens.weight.grad)
         dvis = ops.embed_bwd_vis(dx, pp.vis_src, ctx.n_vis) if ctx.has_vis else None
         ctx.saved = ctx.tape = None
@@ -387,7 +384,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
 
         E = self.model.embed_tokens.weight.data
         x = ops.embed_fwd(pp.ids, E, pp.vis_src if vis is not None else None, vis)
-        hid, _ = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=False, kv_sink=sink)
+        hid_last, _ = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=False, kv_sink=sink, out_rows=pp.last_rows)
         V = self.lm_head.weight.shape[0]
         Vp = (V + 63) // 64 * 64
         logits = torch.empty((B, Vp), dtype=bf16, device=dev)[:, :V]
@@ -432,7 +429,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
                 finished.copy_((fin | (nxt == eos)).to(torch.int32))
             next_ids.copy_(nxt.to(torch.int32))
 
-        head(ops.gather_rows(hid, pp.last_rows))
+        head(hid_last)
         host_ids = [row.tolist() for row in input_ids.cpu()]
         pick(host_ids)
         out_tokens = [next_ids.clone()]

@@ -34,7 +34,7 @@ def test_gemm_matches_fp32_reference(cuda_dev, M, N, K, a_mn, b_mn):
     g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
     a = torch.randn((K, M) if a_mn else (M, K), generator=g).to(cuda_dev, torch.bfloat16)
     b = torch.randn((K, N) if b_mn else (N, K), generator=g).to(cuda_dev, torch.bfloat16)
-    for bn in (128, 256):
+    for bn in (128, 256, 512):                         # 512 = CTA-pair (cta_group::2) kernel
         out = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, block_n=bn)
         torch.cuda.synchronize()
         ref = _ref(a, b, a_mn, b_mn)

@@ -56,7 +56,7 @@ def main():
         C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         flops = 2.0 * M * N * K
         res = {"name": name, "M": M, "N": N, "K": K}
-        for bn in (128, 256):
+        for bn in (256, 512):
             ms = timeit(lambda: ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=C, block_n=bn))
             res[f"nv_bn{bn}_ms"] = ms
             res[f"nv_bn{bn}_tflops"] = flops / ms / 1e9
