@@ -215,13 +215,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       tmem_ld_32x32b_x32(tmem_S + lane_off + 64, *reinterpret_cast<uint32_t(*)[32]>(&s[64]));
       tmem_ld_32x32b_x32(tmem_S + lane_off + 96, *reinterpret_cast<uint32_t(*)[32]>(&s[96]));
       tmem_ld_wait();
-      float m_new = m_run;
+      // four independent running maxima / sums: a single dependent chain of 128 ops would cost ~4 cycles each
+      float mx[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (uint32_t i = 0; i < 128; ++i)
-        if (!diag || i <= r) m_new = fmaxf(m_new, __uint_as_float(s[i]));
+        if (!diag || i <= r) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[i]));
+      const float m_new = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       const float alpha = exp2f((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
-      float rs = 0.f;
+      float rsum[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (uint32_t i = 0; i < 128; i += 2) {
         float p0 = exp2f(__uint_as_float(s[i]) * sl2 - mb);
@@ -233,8 +235,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         // the row sum uses the bf16-rounded probabilities that the PV product actually consumes
         const uint32_t pk = pack_bf16x2(p0, p1);
         s[i >> 1] = pk;
-        rs += bf16_lo(pk) + bf16_hi(pk);
+        rsum[(i >> 1) & 3] += bf16_lo(pk) + bf16_hi(pk);
       }
+      const float rs = (rsum[0] + rsum[1]) + (rsum[2] + rsum[3]);
       if (j > 0) mbar_wait(&pv_done[t], (j - 1) & 1);   // P_t buffer and O_t accumulator free again
       tc_fence_after();
 #pragma unroll

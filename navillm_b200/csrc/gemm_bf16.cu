@@ -283,7 +283,12 @@ extern "C" int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   NV_REQUIRE(!((flags & GEMM_ADD) && (flags & GEMM_OUT_F32)), "nv_gemm_bf16: ADD with fp32 output unsupported");
   NV_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0, "nv_gemm_bf16: lda/ldb must be multiples of 8 (got %lld, %lld)",
              (long long)lda, (long long)ldb);
-  if (block_n == 0) block_n = (N >= 2048) ? 256 : 128;
+  // auto: CTA-pair kernel (256x256 per SM pair) when there is at least one full wave of pair tiles; otherwise
+  // the single-CTA kernel whose smaller tiles give skinny problems (decode, pruned rows) more parallelism
+  if (block_n == 0) {
+    const long pair_tiles = ((long)(M + 255) / 256) * ((long)(N + 255) / 256);
+    block_n = (pair_tiles >= sm_count() / 2 && M >= 512) ? 512 : (N >= 2048 ? 256 : 128);
+  }
   if (block_n == 512)   // CTA-pair kernel (cta_group::2), 256 x 256 tile per SM pair
     return gemm_bf16_2cta_dispatch(A, lda, a_mn, B, ldb, b_mn, C, ldc, addend, ld_add, M, N, K, flags, stream);
   NV_REQUIRE(block_n == 128 || block_n == 256, "nv_gemm_bf16: block_n must be 128, 256 or 512 (2-CTA)");
