@@ -126,6 +126,16 @@ int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, 
                      int pad_id, int stop_on_eos, int* next, int B, void* stream);
 int nv_add_int(int* x, int n, int delta, void* stream);
 
+/* ---- fused clip + AdamW over flat buffers (csrc/optim.cu) ------------------------------------------------------
+ * torch.nn.utils.clip_grad_norm_(model.parameters(), 40.) + torch.optim.AdamW.step() of the reference
+ * (train.py:86-89, tools/optims.py:43) as sum-of-squares partials -> device-side clip coefficient -> one update
+ * pass per flat buffer.  clip_state: fp32 [2] = {grad norm, clip coefficient}. */
+int nv_optim_partials(void);
+int nv_grad_sumsq(const void* g, int64_t n, int is_bf16, float* partial, void* stream);
+int nv_clip_coef(const float* partial, int n_partial, float max_norm, float* state, void* stream);
+int nv_adamw_flat(void* p, void* g, void* m, void* v, int64_t n, int is_bf16, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, int step, const float* clip_state, int write_clipped_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -287,17 +287,18 @@ extern "C" int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   // the single-CTA kernel whose smaller tiles give skinny problems (decode, pruned rows) more parallelism
   if (block_n == 0) {
     const long pair_tiles = ((long)(M + 255) / 256) * ((long)(N + 255) / 256);
-    block_n = (pair_tiles >= sm_count() / 2 && M >= 512) ? 512 : (N >= 2048 ? 256 : 128);
+    block_n = (pair_tiles >= sm_count() / 2 && M >= 512) ? 512 : (M <= 128 && !b_mn) ? 32 : (N >= 2048 ? 256 : 128);
   }
   if (block_n == 512)   // CTA-pair kernel (cta_group::2), 256 x 256 tile per SM pair
     return gemm_bf16_2cta_dispatch(A, lda, a_mn, B, ldb, b_mn, C, ldc, addend, ld_add, M, N, K, flags, stream);
-  NV_REQUIRE(block_n == 128 || block_n == 256, "nv_gemm_bf16: block_n must be 128, 256 or 512 (2-CTA)");
+  NV_REQUIRE(block_n == 32 || block_n == 128 || block_n == 256, "nv_gemm_bf16: block_n must be 32, 128, 256 or 512 (2-CTA)");
 
   CUtensorMap ta, tb;
   int rc;
   if (!a_mn) rc = make_tmap_2d(&ta, A, 2, (uint64_t)K, (uint64_t)M, (uint64_t)lda * 2, 64, GEMM_BLOCK_M);
   else       rc = make_tmap_2d(&ta, A, 2, (uint64_t)M, (uint64_t)K, (uint64_t)lda * 2, 64, GEMM_BLOCK_K);
   if (rc) return rc;
+  NV_REQUIRE(!(block_n == 32 && b_mn), "nv_gemm_bf16: block_n = 32 (skinny-M weight streaming) needs a K-major B");
   if (!b_mn) rc = make_tmap_2d(&tb, B, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldb * 2, 64, (uint32_t)block_n);
   else       rc = make_tmap_2d(&tb, B, 2, (uint64_t)N, (uint64_t)K, (uint64_t)ldb * 2, 64, GEMM_BLOCK_K);
   if (rc) return rc;
@@ -311,6 +312,12 @@ extern "C" int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   } while (0)
 
   if (block_n == 256) NV_GEMM_CASE(256, 4);
+  if (block_n == 32) {
+    // decode / pruned-row GEMMs (M <= 128): HBM-bound weight streaming.  32-column tiles give every projection of
+    // the model >= 128 CTAs, and 10 stages keep ~40 KB of weights in flight per SM.
+    if (!a_mn) return launch_gemm<32, 10, false, false>(ta, tb, C, ldc, addend, ld_add, M, N, K, flags, stream);
+    return launch_gemm<32, 10, true, false>(ta, tb, C, ldc, addend, ld_add, M, N, K, flags, stream);
+  }
   NV_GEMM_CASE(128, 6);
 #undef NV_GEMM_CASE
 }

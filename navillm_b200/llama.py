@@ -335,13 +335,13 @@ class LlamaCore:
         H, D = d.n_heads, d.hidden
         for l, lyr in enumerate(self.model.layers):
             xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
-            qkv = ops.gemm(xn, self.wqkv[l], block_n=128)
+            qkv = ops.gemm(xn, self.wqkv[l], block_n=32)
             ops.rope_(qkv, lens, self.cos, self.sin, 2 * H, d.head_dim)
             ops.kv_append(qkv, lens, kc[l], vc[l])
             ao = ops.decode_attn(qkv, kc[l], vc[l], lens, H)
-            xm = ops.gemm(ao, self.wo[l], addend=x, block_n=128)
+            xm = ops.gemm(ao, self.wo[l], addend=x, block_n=32)
             xn2, _ = ops.rmsnorm_fwd(xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
-            gu = ops.gemm(xn2, self.wgu[l], block_n=128)
+            gu = ops.gemm(xn2, self.wgu[l], block_n=32)
             h = ops.swiglu_fwd(gu)
-            x = ops.gemm(h, self.wd[l], addend=xm, block_n=128)
+            x = ops.gemm(h, self.wd[l], addend=xm, block_n=32)
         return x

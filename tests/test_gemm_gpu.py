@@ -73,3 +73,20 @@ def test_gemm_fp32_out(cuda_dev):
     torch.cuda.synchronize()
     ref = a.float() @ w.float().t()
     assert torch.allclose(out, ref, rtol=1e-4, atol=1e-3), (out - ref).abs().max().item()
+
+
+def test_gemm_skinny_m_weight_streaming(cuda_dev):
+    """block_n = 32 variant used by the decode step and the pruned last layer (M <= 128)."""
+    from navillm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(3)
+    for M, N, K in ((8, 4096, 4096), (16, 22016, 4096), (8, 32006, 4096), (1, 4096, 11008)):
+        a = torch.randn(M, K, generator=g).to(cuda_dev, torch.bfloat16)
+        w = torch.randn(N, K, generator=g).to(cuda_dev, torch.bfloat16)
+        ld = (N + 63) // 64 * 64
+        out = torch.empty(M, ld, device=cuda_dev, dtype=torch.bfloat16)[:, :N]
+        ops.gemm(a, w, out=out, block_n=32)
+        auto = ops.gemm(a, w)
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().t()
+        tol = 1.6e-2 * ref.abs() + 0.2
+        assert bool(((out.float() - ref).abs() <= tol).all()) and bool(((auto.float() - ref).abs() <= tol).all())
