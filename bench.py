@@ -46,8 +46,8 @@ LEN_LO, LEN_HI = 256, 1024
 
 def gemm_traffic():
     """Average DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_gemm_ncu_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of GEMM launches inside a step)."""
-    p = ROOT / "profiles" / "r01_gemm_ncu_summary.json"
+    (profiles/r01_gemm2cta_ncu_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of GEMM launches inside a step)."""
+    p = ROOT / "profiles" / "r01_gemm2cta_ncu_summary.json"
     if not p.exists():
         return None, None
     unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
@@ -346,8 +346,9 @@ def main():
         ms = timed(step_resident, a.steps)
     timer, ops.gemm_timer = ops.gemm_timer, None
     launches = (_lib.launch_count - launches0) // max(a.steps, 1)
-    gemm_ms = sum(s.elapsed_time(e) for s, e, _ in timer)
-    gemm_flops = sum(f for _, _, f in timer)
+    gemm_ms = sum(t[0].elapsed_time(t[1]) for t in timer)
+    gemm_flops = sum(t[2] for t in timer)
+    gemm_bytes = sum(t[3] for t in timer)
     n_gemm = len(timer)
 
     if a.profile:
@@ -377,11 +378,11 @@ def main():
             "e2e": {"value": e2e, "unit": "nav-steps/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05_2cta (cta_group::2; skinny launches use gemm_bf16_tcgen05)", "achieved": achieved, "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
                          "frac": (achieved / pk["bf16_tflops"]) if achieved else None, "peak_src": pk["src"] + " (sustained cuBLAS bf16)",
                          "launches_per_step": n_gemm // max(a.steps, 1), "share_of_step": gemm_ms / ms,
                          "traffic": gemm_traffic()[0], "traffic_unit": "bytes/launch (DRAM read+write)", "traffic_src": gemm_traffic()[1],
-                         "algorithmic_bytes_per_launch_mean": None,
+                         "algorithmic_bytes_per_launch_mean": gemm_bytes / max(n_gemm, 1),
                          "step_algorithmic_tflop": algo_step / 1e12,
                          "step_frac_of_peak": algo_step / 1e12 / (ms / a.steps / 1e3) / pk["bf16_tflops"]},
             "clocks": clk.summary(),

@@ -396,7 +396,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
 
         def head(h_rows):
             hn, _ = ops.rmsnorm_fwd(h_rows, self.model.norm.weight.data, d.rms_eps)
-            ops.gemm(hn, self.lm_head.weight.data, out=logits, block_n=32)
+            ops.gemm(hn, self.lm_head.weight.data, out=logits, block_n=128)
 
         trie_state = [None]
 

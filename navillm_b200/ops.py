@@ -55,7 +55,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
                            i32(M), i32(N), i32(K), u32(flags), i32(block_n), stream_ptr()), "nv_gemm_bf16")
     if timer is not None:
         en.record()
-        timer.append((st, en, 2.0 * M * N * K))
+        timer.append((st, en, 2.0 * M * N * K, 2.0 * (M * K + N * K + M * N * (2 if addend is not None else 1))))
     return out
 
 
