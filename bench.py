@@ -203,7 +203,7 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------
 # CPU arm: oracle port of the reference on host cores (bounded sample)
 # ---------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(n_layers: int, seq: int, reps: int = 1):
+def cpu_reference_sample(n_layers: int, seq: int, reps: int = 1, warm: int = 1):
     from oracle import navillm_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -222,28 +222,26 @@ def cpu_reference_sample(n_layers: int, seq: int, reps: int = 1):
     emb = torch.randn(1, seq, D_MODEL, generator=g).to(torch.bfloat16).requires_grad_(True)
     mask = torch.ones(1, seq, dtype=torch.long)
     times = []
-    for _ in range(reps + 1):                                       # first pass = warm-up
+    for _ in range(warm + reps):                                    # `warm` untimed passes first
         t0 = time.perf_counter()
         h = O.llama_model(sd, cfg, emb, mask)
         h[:, -1].float().sum().backward()
         times.append(time.perf_counter() - t0)
-    t_layers = min(times[1:]) if reps else times[0]
+    t_layers = statistics.median(times[warm:])
     per_layer = t_layers / n_layers
     t_step = per_layer * N_LAYERS                                    # pano encoder + heads are < 0.1 % of the FLOPs
     return {"nav_steps_per_s": 1.0 / t_step, "seconds_per_step": t_step, "cores": cores,
             "sample": f"oracle port (bf16 LM like the reference 'amp_bf16'), B=1, seq={seq} (workload mean length), "
-                      f"{n_layers} of {N_LAYERS} full-width Vicuna-7B layers fwd+bwd timed ({t_layers:.2f} s) and scaled x{N_LAYERS}/{n_layers}"}
+                      f"{n_layers} of {N_LAYERS} full-width Vicuna-7B layers fwd+bwd timed (median of {reps}: {t_layers:.2f} s) "
+                      f"and scaled x{N_LAYERS}/{n_layers}"}
 
 
 def run_reference_arm(a, rank, world):
     if rank != 0:
         return
     mean_len = (LEN_LO + LEN_HI) // 2
-    vals = []
-    for _ in range(max(a.steps, 1)):
-        r = cpu_reference_sample(a.cpu_layers, mean_len, reps=1)
-        vals.append(r["nav_steps_per_s"])
-    v = statistics.median(vals)
+    r = cpu_reference_sample(a.cpu_layers, mean_len, reps=max(a.steps, 1), warm=max(min(a.warmup, 2), 1))
+    v = r["nav_steps_per_s"]
     line = {"impl": "reference", "metric": "nav_steps_per_sec", "value": v, "unit": "nav-steps/s", "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000.0 * B_STEP / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",

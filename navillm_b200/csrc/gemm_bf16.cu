@@ -287,7 +287,7 @@ extern "C" int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   // the single-CTA kernel whose smaller tiles give skinny problems (decode, pruned rows) more parallelism
   if (block_n == 0) {
     const long pair_tiles = ((long)(M + 255) / 256) * ((long)(N + 255) / 256);
-    block_n = (pair_tiles >= sm_count() / 2 && M >= 512) ? 512 : (M <= 128 && !b_mn && N <= 4096) ? 32 : (M <= 128 ? 128 : (N >= 2048 ? 256 : 128));
+    block_n = (pair_tiles >= sm_count() / 2 && M >= 512) ? 512 : (M <= 128) ? 128 : (N >= 2048 ? 256 : 128);
   }
   if (block_n == 512)   // CTA-pair kernel (cta_group::2), 256 x 256 tile per SM pair
     return gemm_bf16_2cta_dispatch(A, lda, a_mn, B, ldb, b_mn, C, ldc, addend, ld_add, M, N, K, flags, stream);

@@ -333,18 +333,19 @@ class LlamaCore:
         [B, D] before the final RMSNorm."""
         d = self.d
         H, D = d.n_heads, d.hidden
-        # tile widths for M <= 128 (HBM-bound weight streaming): N = 4096 projections get 32-column tiles (128 CTAs);
-        # the wide ones keep 128-column tiles, where re-filling the (mostly zero) activation tile per k-block is
-        # amortised over 4x more weight bytes (measured: 32-wide tiles everywhere are 2x slower)
+        # M <= 128 is HBM-bound weight streaming.  Measured on B200 (tools/decode_bench.py, C3): 128-column tiles
+        # 5.9 ms/token; 32-column tiles (more CTAs for the N = 4096 projections) 8.8-12.2 ms/token -- re-filling the
+        # (mostly zero) 128-row activation tile per k-block costs more than the extra CTAs gain.  A swap-AB /
+        # split-K skinny kernel is the planned fix; until then 128-column tiles.
         for l, lyr in enumerate(self.model.layers):
             xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
             qkv = ops.gemm(xn, self.wqkv[l], block_n=128)
             ops.rope_(qkv, lens, self.cos, self.sin, 2 * H, d.head_dim)
             ops.kv_append(qkv, lens, kc[l], vc[l])
             ao = ops.decode_attn(qkv, kc[l], vc[l], lens, H)
-            xm = ops.gemm(ao, self.wo[l], addend=x, block_n=32)
+            xm = ops.gemm(ao, self.wo[l], addend=x, block_n=128)
             xn2, _ = ops.rmsnorm_fwd(xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
             gu = ops.gemm(xn2, self.wgu[l], block_n=128)
             h = ops.swiglu_fwd(gu)
-            x = ops.gemm(h, self.wd[l], addend=xm, block_n=32)
+            x = ops.gemm(h, self.wd[l], addend=xm, block_n=128)
         return x

@@ -61,11 +61,13 @@ class FlatAdamW:
 
     # ---- torch.optim-compatible (de)serialisation ----
     def _named_views(self, bufs):
-        out = []
+        """Per-parameter views of the flat moment buffers, in ``model.parameters()`` order (the order
+        torch.optim.AdamW([p for n, p in model.named_parameters() if p.requires_grad]) indexes its state by)."""
+        where = {}
         for f, buf in zip(self.flats, bufs):
             for p, o in zip(f.params, f.offsets):
-                out.append(buf[o:o + p.numel()].view(p.shape))
-        return out
+                where[id(p)] = buf[o:o + p.numel()].view(p.shape)
+        return [where[id(p)] for p in self.model.parameters() if p.requires_grad and id(p) in where]
 
     def state_dict(self):
         ms, vs = self._named_views(self.m), self._named_views(self.v)
