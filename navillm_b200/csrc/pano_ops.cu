@@ -22,17 +22,22 @@ namespace nv {
 constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
 enum { SG_ACCUM = 1 };
 
+// blockIdx.z = K split: each split handles a contiguous k range and (when there are several) adds its partial
+// with fp32 atomics into a C that already holds the accumulate-into value (or zeros).
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t lda, int ta,
                                                     const float* __restrict__ B, int64_t ldb, int tb,
                                                     float* __restrict__ C, int64_t ldc, const float* __restrict__ bias,
-                                                    int M, int N, int K, int flags) {
+                                                    int M, int N, int K, int flags, int k_per_split) {
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Bs[SG_BK][SG_BN + 4];
   const int tid = threadIdx.x;
   const int m0 = blockIdx.y * SG_BM, n0 = blockIdx.x * SG_BN;
   const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4x4 outputs
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += SG_BK) {
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const bool split = gridDim.z > 1;
+  for (int k0 = k_begin; k0 < k_end; k0 += SG_BK) {
     // load A tile (64 x 16) and B tile (16 x 64): 1024 elements each, 4 per thread
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -42,14 +47,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
         const int mm = ta ? (e & 63) : (e >> 4), kk = ta ? (e >> 6) : (e & 15);
         const int gm = m0 + mm, gk = k0 + kk;
         float v = 0.f;
-        if (gm < M && gk < K) v = ta ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
+        if (gm < M && gk < k_end) v = ta ? A[(int64_t)gk * lda + gm] : A[(int64_t)gm * lda + gk];
         As[kk][mm] = v;
       }
       {
         const int nn = tb ? (e & 63) : (e >> 4), kk = tb ? (e >> 6) : (e & 15);
         const int gn = n0 + nn, gk = k0 + kk;
         float v = 0.f;
-        if (gn < N && gk < K) v = tb ? B[(int64_t)gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
+        if (gn < N && gk < k_end) v = tb ? B[(int64_t)gk * ldb + gn] : B[(int64_t)gn * ldb + gk];
         Bs[kk][nn] = v;
       }
     }
@@ -77,10 +82,14 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = acc[i][j];
-      if (bias) v += bias[gn];
+      if (bias && blockIdx.z == 0) v += bias[gn];
       float* c = C + (int64_t)gm * ldc + gn;
-      if (flags & SG_ACCUM) v += *c;
-      *c = v;
+      if (split) {
+        atomicAdd(c, v);                 // C was zeroed (or holds the accumulate-into value) by the host wrapper
+      } else {
+        if (flags & SG_ACCUM) v += *c;
+        *c = v;
+      }
     }
   }
 }
@@ -371,8 +380,17 @@ int nv_sgemm(const float* A, int64_t lda, int ta, const float* B, int64_t ldb, i
              const float* bias, int M, int N, int K, int accumulate, void* stream) {
   if (M == 0 || N == 0) return NV_OK;
   NV_REQUIRE(M > 0 && N > 0 && K > 0 && A && B && C, "nv_sgemm: bad arguments M=%d N=%d K=%d", M, N, K);
-  dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM);
-  sgemm_kernel<<<grid, 256, 0, S_(stream)>>>(A, lda, ta, B, ldb, tb, C, ldc, bias, M, N, K, accumulate ? SG_ACCUM : 0);
+  dim3 grid((N + SG_BN - 1) / SG_BN, (M + SG_BM - 1) / SG_BM, 1);
+  // Encoder GEMMs are small (<= a few hundred tiles, K up to 4096): split K until ~3 CTAs per SM are in flight.
+  const int tiles = grid.x * grid.y;
+  int splits = 1;
+  while (splits < 8 && tiles * splits < 3 * sm_count() && K / (splits * 2) >= 256) splits *= 2;
+  int k_per_split = ((K + splits - 1) / splits + SG_BK - 1) / SG_BK * SG_BK;
+  grid.z = (K + k_per_split - 1) / k_per_split;
+  if (grid.z > 1 && !accumulate)
+    NV_CUDA(cudaMemset2DAsync(C, ldc * sizeof(float), 0, (size_t)N * sizeof(float), (size_t)M, S_(stream)));
+  sgemm_kernel<<<grid, 256, 0, S_(stream)>>>(A, lda, ta, B, ldb, tb, C, ldc, bias, M, N, K, accumulate ? SG_ACCUM : 0,
+                                             k_per_split);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }
