@@ -46,6 +46,17 @@ int nv_sm_count(void);
 int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ldb, int b_mn, void* C, int64_t ldc,
                  const void* addend, int64_t ld_add, int M, int N, int K, unsigned flags, int block_n, void* stream);
 
+/* Fused-epilogue forms on the CTA-pair kernel (csrc/gemm_bf16_2cta.cu), bit-identical to the unfused sequences:
+ *   nv_gemm_swiglu_bf16   gu = x Wgu^T and h = silu(gate)*up        (HF LlamaMLP: act_fn(gate_proj(x)) * up_proj(x))
+ *   nv_gemm_dswiglu_bf16  dgu = swiglu'(gu) o (dx Wd)               (autograd of the above through down_proj)
+ *   nv_gemm_rope_bf16     qkv = x Wqkv^T with rotate-half RoPE on the q,k columns (HF apply_rotary_pos_emb) */
+int nv_gemm_swiglu_bf16(const void* x, int64_t ldx, const void* Wgu, int64_t ldw, void* gu, int64_t ldgu, void* h,
+                        int64_t ldh, int M, int F, int K, int keep_gu, void* stream);
+int nv_gemm_dswiglu_bf16(const void* dx, int64_t lddx, const void* Wd, int64_t ldw, const void* gu, int64_t ldgu, void* dgu,
+                         int64_t lddgu, int M, int F, int D, void* stream);
+int nv_gemm_rope_bf16(const void* x, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, const int* pos,
+                      const void* cos_t, const void* sin_t, int M, int N, int K, int rope_cols, void* stream);
+
 /* ---- flash attention on packed rows (csrc/attn_fwd.cu, attn_bwd.cu) ------------------------------------
  * Causal self-attention of HF LlamaAttention (eager softmax(QK^T/sqrt(d)+mask)V; call site
  * models/modified_lm.py:112-116) and its backward (loss.backward(): tasks/agents/mp3d_agent.py:750-757).

@@ -93,11 +93,34 @@ __device__ __forceinline__ void tile_coords2(uint32_t tile, uint32_t num_m, uint
   n_blk = r / gm;
 }
 
-template <bool A_MN, bool B_MN>
+// Fused epilogues (EPI):
+//   EPI_PLAIN   C = bf16(acc) (+addend) | fp32(acc)
+//   EPI_SWIGLU  gate|up projection: the pair tile holds 128 gate columns (CTA 0's half of B = gate rows) and the
+//               SAME 128 up columns (CTA 1's half = up rows F + n); writes g,u into the fused [T,2F] buffer (kept
+//               for the backward) and h = bf16(bf16(silu(g)) * u) into aux [T,F]   (HF LlamaMLP act_fn(gate)*up)
+//   EPI_DSWIGLU down-projection dgrad: acc = dh; reads g,u from aux [T,2F] and writes dg = dh*u*silu'(g),
+//               du = dh*silu(g) into C [T,2F] (the separate swiglu_bwd pass and the dh round trip disappear)
+//   EPI_ROPE    fused q|k|v projection: columns < rope_cols get the rotate-half rotary embedding
+//               (HF apply_rotary_pos_emb, bf16 rounding points preserved) with cos/sin[pos[row]] before the store
+enum { EPI_PLAIN = 0, EPI_SWIGLU = 1, EPI_DSWIGLU = 2, EPI_ROPE = 3 };
+
+struct EpiAux {
+  void* aux;            // SWIGLU: h out [T,F];  DSWIGLU: gu in [T,2F]
+  int64_t ld_aux;
+  uint32_t F;           // SWIGLU / DSWIGLU: intermediate size (columns of gate and of up)
+  const int* pos;       // ROPE
+  const __nv_bfloat16* cos_t;
+  const __nv_bfloat16* sin_t;
+  uint32_t rope_cols;   // ROPE: q and k columns (2 * H * 128)
+};
+
+__device__ __forceinline__ float silu_bf16(float g) { return bf16_round(g / (1.f + __expf(-g))); }
+
+template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        void* __restrict__ Cout, int64_t ldc, const __nv_bfloat16* __restrict__ addend, int64_t ld_add,
-                       uint32_t M, uint32_t N, uint32_t K, uint32_t flags) {
+                       uint32_t M, uint32_t N, uint32_t K, uint32_t flags, EpiAux ea) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -136,8 +159,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // logical output columns per pair tile: 256, except SWIGLU where the 256 accumulator columns are 128 gate + 128 up
+  constexpr uint32_t TILE_N = (EPI == EPI_SWIGLU) ? 128u : G2_BN;
   const uint32_t num_m = ceil_div_u32(M, 2 * G2_BM);
-  const uint32_t num_n = ceil_div_u32(N, G2_BN);
+  const uint32_t num_n = ceil_div_u32(N, TILE_N);
   const uint32_t num_tiles = num_m * num_n;
   const uint32_t num_kb = ceil_div_u32(K, G2_BK);
   const uint32_t cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
@@ -150,7 +175,8 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         uint32_t m_blk, n_blk;
         tile_coords2(tile, num_m, num_n, m_blk, n_blk);
         const int32_t m0 = m_blk * 2 * G2_BM + rank * G2_BM;    // this CTA's A rows
-        const int32_t n0 = n_blk * G2_BN + rank * G2_BNH;       // this CTA's half of the B tile
+        // this CTA's half of the B tile (SWIGLU: CTA 0 stages gate rows n.., CTA 1 the matching up rows F + n..)
+        const int32_t n0 = (EPI == EPI_SWIGLU) ? (int32_t)(n_blk * 128 + rank * ea.F) : (int32_t)(n_blk * G2_BN + rank * G2_BNH);
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
@@ -216,8 +242,124 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t row = m_blk * 2 * G2_BM + rank * G2_BM + quarter * 32 + lane;
-      const uint32_t col0 = n_blk * G2_BN;
+      const uint32_t col0 = n_blk * TILE_N;
       const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + acc * G2_BN;
+      if constexpr (EPI == EPI_SWIGLU) {
+        __nv_bfloat16* gu = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<int64_t>(row) * ldc;
+        __nv_bfloat16* hrow = reinterpret_cast<__nv_bfloat16*>(ea.aux) + static_cast<int64_t>(row) * ea.ld_aux;
+#pragma unroll 1
+        for (uint32_t c = 0; c < 128; c += 32) {
+          uint32_t g[32], u[32];
+          tmem_ld_32x32b_x32(taddr + c, g);
+          tmem_ld_32x32b_x32(taddr + 128 + c, u);
+          tmem_ld_wait();
+          const uint32_t col = col0 + c;
+          if (row < M && col < ea.F) {   // F % 32 == 0 is required by the host wrapper
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j += 8) {
+              uint4 og, ou, oh;
+              uint32_t* pg = &og.x; uint32_t* pu = &ou.x; uint32_t* ph = &oh.x;
+#pragma unroll
+              for (uint32_t q = 0; q < 4; ++q) {
+                pg[q] = pack_bf16x2(__uint_as_float(g[j + 2 * q]), __uint_as_float(g[j + 2 * q + 1]));
+                pu[q] = pack_bf16x2(__uint_as_float(u[j + 2 * q]), __uint_as_float(u[j + 2 * q + 1]));
+                ph[q] = pack_bf16x2(silu_bf16(bf16_lo(pg[q])) * bf16_lo(pu[q]), silu_bf16(bf16_hi(pg[q])) * bf16_hi(pu[q]));
+              }
+              if ((flags & 4u) == 0) {                                   // flag 4: inference, do not keep g|u
+                *reinterpret_cast<uint4*>(gu + col + j) = og;
+                *reinterpret_cast<uint4*>(gu + ea.F + col + j) = ou;
+              }
+              *reinterpret_cast<uint4*>(hrow + col + j) = oh;
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_DSWIGLU) {
+        __nv_bfloat16* dgu = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<int64_t>(row) * ldc;
+        const __nv_bfloat16* gu = reinterpret_cast<const __nv_bfloat16*>(ea.aux) + static_cast<int64_t>(row) * ea.ld_aux;
+#pragma unroll 1
+        for (uint32_t c = 0; c < G2_BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c, v);
+          tmem_ld_wait();
+          const uint32_t col = col0 + c;
+          if (row < M && col < ea.F) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j += 8) {
+              const uint4 gg = *reinterpret_cast<const uint4*>(gu + col + j);
+              const uint4 uu = *reinterpret_cast<const uint4*>(gu + ea.F + col + j);
+              const uint32_t* pg = &gg.x; const uint32_t* pu = &uu.x;
+              uint4 og, ou;
+              uint32_t* qg = &og.x; uint32_t* qu = &ou.x;
+#pragma unroll
+              for (uint32_t q = 0; q < 4; ++q) {
+                float dg[2], du[2];
+#pragma unroll
+                for (uint32_t e = 0; e < 2; ++e) {
+                  const float d = bf16_round(__uint_as_float(v[j + 2 * q + e]));   // dh as the unfused path stores it
+                  const float gv = e ? bf16_hi(pg[q]) : bf16_lo(pg[q]);
+                  const float uv = e ? bf16_hi(pu[q]) : bf16_lo(pu[q]);
+                  const float sg = 1.f / (1.f + __expf(-gv));
+                  dg[e] = d * uv * (sg * (1.f + gv * (1.f - sg)));
+                  du[e] = d * (gv * sg);
+                }
+                qg[q] = pack_bf16x2(dg[0], dg[1]);
+                qu[q] = pack_bf16x2(du[0], du[1]);
+              }
+              *reinterpret_cast<uint4*>(dgu + col + j) = og;
+              *reinterpret_cast<uint4*>(dgu + ea.F + col + j) = ou;
+            }
+          }
+        }
+      } else if constexpr (EPI == EPI_ROPE) {
+        __nv_bfloat16* crow = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<int64_t>(row) * ldc;
+        const int p = (row < M) ? ea.pos[row] : 0;
+        const __nv_bfloat16* cs = ea.cos_t + static_cast<int64_t>(p) * 128;
+        const __nv_bfloat16* sn = ea.sin_t + static_cast<int64_t>(p) * 128;
+#pragma unroll 1
+        for (uint32_t hh = 0; hh < G2_BN; hh += 128) {        // two 128-wide heads per tile
+#pragma unroll 1
+          for (uint32_t c = 0; c < 64; c += 32) {              // chunk c pairs with chunk c + 64 (rotate-half)
+            uint32_t a[32], b[32];
+            tmem_ld_32x32b_x32(taddr + hh + c, a);
+            tmem_ld_32x32b_x32(taddr + hh + 64 + c, b);
+            tmem_ld_wait();
+            const uint32_t col = col0 + hh + c;
+            if (row < M && col < N) {
+              const bool rope = col < ea.rope_cols;
+#pragma unroll
+              for (uint32_t j = 0; j < 32; j += 8) {
+                uint4 o1, o2;
+                uint32_t* p1 = &o1.x; uint32_t* p2 = &o2.x;
+                uint4 c1 = make_uint4(0, 0, 0, 0), s1 = c1, c2 = c1, s2 = c1;
+                if (rope) {
+                  c1 = *reinterpret_cast<const uint4*>(cs + c + j);      s1 = *reinterpret_cast<const uint4*>(sn + c + j);
+                  c2 = *reinterpret_cast<const uint4*>(cs + 64 + c + j); s2 = *reinterpret_cast<const uint4*>(sn + 64 + c + j);
+                }
+                const uint32_t* pc1 = &c1.x; const uint32_t* ps1 = &s1.x; const uint32_t* pc2 = &c2.x; const uint32_t* ps2 = &s2.x;
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) {
+                  // projection output rounded to bf16 first (the reference ropes the bf16 q/k)
+                  const uint32_t xa = pack_bf16x2(__uint_as_float(a[j + 2 * q]), __uint_as_float(a[j + 2 * q + 1]));
+                  const uint32_t xb = pack_bf16x2(__uint_as_float(b[j + 2 * q]), __uint_as_float(b[j + 2 * q + 1]));
+                  if (rope) {
+                    const float y1l = bf16_round(bf16_lo(xa) * bf16_lo(pc1[q])) + bf16_round(-bf16_lo(xb) * bf16_lo(ps1[q]));
+                    const float y1h = bf16_round(bf16_hi(xa) * bf16_hi(pc1[q])) + bf16_round(-bf16_hi(xb) * bf16_hi(ps1[q]));
+                    const float y2l = bf16_round(bf16_lo(xb) * bf16_lo(pc2[q])) + bf16_round(bf16_lo(xa) * bf16_lo(ps2[q]));
+                    const float y2h = bf16_round(bf16_hi(xb) * bf16_hi(pc2[q])) + bf16_round(bf16_hi(xa) * bf16_hi(ps2[q]));
+                    p1[q] = pack_bf16x2(y1l, y1h);
+                    p2[q] = pack_bf16x2(y2l, y2h);
+                  } else {
+                    p1[q] = xa;
+                    p2[q] = xb;
+                  }
+                }
+                *reinterpret_cast<uint4*>(crow + col + j) = o1;
+                *reinterpret_cast<uint4*>(crow + col + 64 + j) = o2;
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (uint32_t c = 0; c < G2_BN; c += 32) {
         uint32_t v[32];
@@ -269,6 +411,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -286,19 +429,20 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int EPI = EPI_PLAIN>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int64_t ldc, const void* addend,
-                            int64_t ld_add, uint32_t M, uint32_t N, uint32_t K, uint32_t flags, cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05_2cta<A_MN, B_MN>;
+                            int64_t ld_add, uint32_t M, uint32_t N, uint32_t K, uint32_t flags, cudaStream_t stream,
+                            EpiAux ea = EpiAux{}) {
+  auto kern = gemm_bf16_tcgen05_2cta<A_MN, B_MN, EPI>;
   static bool attr_set = false;
   if (!attr_set) {
     NV_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_DYN_BYTES));
     attr_set = true;
   }
-  const uint32_t tiles = ceil_div_u32(M, 2 * G2_BM) * ceil_div_u32(N, G2_BN);
+  const uint32_t tiles = ceil_div_u32(M, 2 * G2_BM) * ceil_div_u32(N, EPI == EPI_SWIGLU ? 128u : G2_BN);
   uint32_t clusters = min(tiles, (uint32_t)sm_count() / 2);
   kern<<<clusters * 2, G2_THREADS, G2_DYN_BYTES, stream>>>(ta, tb, C, ldc, reinterpret_cast<const __nv_bfloat16*>(addend),
-                                                            ld_add, M, N, K, flags);
+                                                            ld_add, M, N, K, flags, ea);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }
@@ -322,3 +466,57 @@ int gemm_bf16_2cta_dispatch(const void* A, int64_t lda, int a_mn, const void* B,
 }
 
 }  // namespace nv
+
+// ---- fused-epilogue entry points (K-major activations x nn.Linear weights; full-wave problems) -----------------
+extern "C" {
+
+// gu[T, 2F] = x[T,K] · Wgu[2F,K]^T  (gate rows then up rows)  and  h[T,F] = silu(g) * u   in one kernel.
+int nv_gemm_swiglu_bf16(const void* x, int64_t ldx, const void* Wgu, int64_t ldw, void* gu, int64_t ldgu, void* h,
+                        int64_t ldh, int M, int F, int K, int keep_gu, void* stream) {
+  using namespace nv;
+  NV_REQUIRE(M > 0 && F > 0 && K > 0 && (F % 128) == 0, "nv_gemm_swiglu_bf16: F must be a multiple of 128 (got %d)", F);
+  NV_REQUIRE((ldx & 7) == 0 && (ldw & 7) == 0 && (ldgu & 7) == 0 && (ldh & 7) == 0, "nv_gemm_swiglu_bf16: alignment");
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, x, 2, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, G2_BM))) return rc;
+  if ((rc = make_tmap_2d(&tb, Wgu, 2, (uint64_t)K, (uint64_t)2 * F, (uint64_t)ldw * 2, 64, G2_BNH))) return rc;
+  EpiAux ea{};
+  ea.aux = h; ea.ld_aux = ldh; ea.F = (uint32_t)F;
+  return launch_gemm_2cta<false, false, EPI_SWIGLU>(ta, tb, gu, ldgu, nullptr, 0, M, F, K, keep_gu ? 0u : 4u,
+                                                    reinterpret_cast<cudaStream_t>(stream), ea);
+}
+
+// dgu[T,2F] = swiglu'(gu) applied to dh = dx[T,D] · Wd[D,F]   (Wd is the nn.Linear weight [D, F]: B stored [K=D, N=F]).
+int nv_gemm_dswiglu_bf16(const void* dx, int64_t lddx, const void* Wd, int64_t ldw, const void* gu, int64_t ldgu, void* dgu,
+                         int64_t lddgu, int M, int F, int D, void* stream) {
+  using namespace nv;
+  NV_REQUIRE(M > 0 && F > 0 && D > 0 && (F % 32) == 0, "nv_gemm_dswiglu_bf16: F %% 32");
+  NV_REQUIRE((lddx & 7) == 0 && (ldw & 7) == 0 && (ldgu & 7) == 0 && (lddgu & 7) == 0, "nv_gemm_dswiglu_bf16: alignment");
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, dx, 2, (uint64_t)D, (uint64_t)M, (uint64_t)lddx * 2, 64, G2_BM))) return rc;
+  if ((rc = make_tmap_2d(&tb, Wd, 2, (uint64_t)F, (uint64_t)D, (uint64_t)ldw * 2, 64, G2_BK))) return rc;
+  EpiAux ea{};
+  ea.aux = const_cast<void*>(gu); ea.ld_aux = ldgu; ea.F = (uint32_t)F;
+  return launch_gemm_2cta<false, true, EPI_DSWIGLU>(ta, tb, dgu, lddgu, nullptr, 0, M, F, D, 0u,
+                                                    reinterpret_cast<cudaStream_t>(stream), ea);
+}
+
+// qkv[T, N] = x[T,K] · Wqkv[N,K]^T with rotate-half RoPE applied to the first rope_cols columns (q and k heads).
+int nv_gemm_rope_bf16(const void* x, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, const int* pos,
+                      const void* cos_t, const void* sin_t, int M, int N, int K, int rope_cols, void* stream) {
+  using namespace nv;
+  NV_REQUIRE(M > 0 && N > 0 && K > 0 && (N % 128) == 0 && (rope_cols % 128) == 0, "nv_gemm_rope_bf16: head alignment");
+  NV_REQUIRE((ldx & 7) == 0 && (ldw & 7) == 0 && (ldo & 7) == 0, "nv_gemm_rope_bf16: alignment");
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, x, 2, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, G2_BM))) return rc;
+  if ((rc = make_tmap_2d(&tb, W, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, G2_BNH))) return rc;
+  EpiAux ea{};
+  ea.pos = pos; ea.cos_t = reinterpret_cast<const __nv_bfloat16*>(cos_t); ea.sin_t = reinterpret_cast<const __nv_bfloat16*>(sin_t);
+  ea.rope_cols = (uint32_t)rope_cols;
+  return launch_gemm_2cta<false, false, EPI_ROPE>(ta, tb, out, ldo, nullptr, 0, M, N, K, 0u,
+                                                  reinterpret_cast<cudaStream_t>(stream), ea);
+}
+
+}  // extern "C"

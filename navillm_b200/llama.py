@@ -225,6 +225,7 @@ class LlamaCore:
             self.wd.append(m.down_proj.weight.data)
             self.gd.append(m.down_proj.weight.grad)
         self.cos, self.sin = rope_tables(dims, flat.flat.device)
+        self.fused_epilogues = True
 
     # -------------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True, kv_sink=None,
@@ -242,12 +243,17 @@ class LlamaCore:
         H = d.n_heads
         saved: List[_Saved] = []
         last = d.n_layers - 1
+        # fused-epilogue kernels (CTA-pair GEMM) need head_dim 128, F % 128 == 0 and at least one wave of tiles
+        fused = self.fused_epilogues and x.shape[0] >= 1024 and d.inter % 128 == 0 and d.hidden % 256 == 0
         for l, lyr in enumerate(self.model.layers):
             s = _Saved()
             s.x = x
             s.xn, s.rstd1 = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
-            s.qkv = ops.gemm(s.xn, self.wqkv[l])
-            ops.rope_(s.qkv, pos, self.cos, self.sin, 2 * H, d.head_dim)
+            if fused:
+                s.qkv = ops.gemm_rope(s.xn, self.wqkv[l], pos, self.cos, self.sin, 2 * d.hidden)   # RoPE in the epilogue
+            else:
+                s.qkv = ops.gemm(s.xn, self.wqkv[l])
+                ops.rope_(s.qkv, pos, self.cos, self.sin, 2 * H, d.head_dim)
             if kv_sink is not None:
                 kv_sink(l, s.qkv)                      # prefill of generate(): post-RoPE K,V go to the cache
             s.ao, s.lse = ops.attn_fwd(s.qkv, cu, seqlens, H)
@@ -259,8 +265,11 @@ class LlamaCore:
                 xin = ops.gather_rows(x, out_rows)
             s.xm = ops.gemm(ao, self.wo[l], addend=xin)
             s.xn2, s.rstd2 = ops.rmsnorm_fwd(s.xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
-            s.gu = ops.gemm(s.xn2, self.wgu[l])
-            s.h = ops.swiglu_fwd(s.gu)
+            if fused and s.rows is None:
+                s.gu, s.h = ops.gemm_swiglu(s.xn2, self.wgu[l])                                    # SwiGLU in the epilogue
+            else:
+                s.gu = ops.gemm(s.xn2, self.wgu[l])
+                s.h = ops.swiglu_fwd(s.gu)
             x = ops.gemm(s.h, self.wd[l], addend=s.xm)
             if save:
                 saved.append(s)
@@ -286,10 +295,13 @@ class LlamaCore:
         for l in range(d.n_layers - 1, -1, -1):
             lyr, s = self.model.layers[l], saved[l]
             # ---- MLP:  x_out = xm + down(swiglu(gate_up(rmsnorm2(xm)))) ----
-            dh = ops.gemm(dx, self.wd[l], b_mn=True)                                   # [T,F]  dgrad
+            if self.fused_epilogues and dx.shape[0] >= 1024 and d.inter % 32 == 0:
+                dgu = ops.gemm_dswiglu(dx, self.wd[l], s.gu)                           # dgrad + SwiGLU' in the epilogue
+            else:
+                dh = ops.gemm(dx, self.wd[l], b_mn=True)                               # [T,F]  dgrad
+                dgu = ops.swiglu_bwd(s.gu, dh)
+                del dh
             ops.gemm(dx, s.h, a_mn=True, b_mn=True, out=self.gd[l], addend=add(self.gd[l]))  # dWd += dx^T h
-            dgu = ops.swiglu_bwd(s.gu, dh)
-            del dh
             dxn2 = ops.gemm(dgu, self.wgu[l], b_mn=True)                               # [T,D]
             ops.gemm(dgu, s.xn2, a_mn=True, b_mn=True, out=self.ggu[l], addend=add(self.ggu[l]))
             del dgu

@@ -430,3 +430,65 @@ def argmax_masked(logits, special, finished, eos_id, pad_id, stop_on_eos, next_i
 def add_int_(x, delta):
     check(_lib.load().nv_add_int(ptr(x), i32(x.numel()), i32(delta), stream_ptr()), "nv_add_int")
     return x
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused-epilogue GEMMs on the CTA-pair kernel (csrc/gemm_bf16_2cta.cu)
+# ---------------------------------------------------------------------------------------------------
+def _timed(fn, flops, nbytes):
+    timer = gemm_timer
+    if timer is None:
+        return fn()
+    st, en = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    st.record()
+    r = fn()
+    en.record()
+    timer.append((st, en, flops, nbytes))
+    return r
+
+
+def gemm_swiglu(x, wgu, *, gu=None, h=None, keep_gu=True):
+    """gu = x·Wgu^T ([T,2F]: gate | up) and h = silu(gate)*up ([T,F]) in ONE kernel (SwiGLU epilogue)."""
+    _rowmajor(x, "x"); _rowmajor(wgu, "wgu")
+    T, K = x.shape
+    F = wgu.shape[0] // 2
+    if gu is None:
+        gu = torch.empty((T, 2 * F), dtype=bf16, device=x.device)
+    if h is None:
+        h = torch.empty((T, F), dtype=bf16, device=x.device)
+    lib = _lib.load()
+    _timed(lambda: check(lib.nv_gemm_swiglu_bf16(ptr(x), i64(x.stride(0)), ptr(wgu), i64(wgu.stride(0)), ptr(gu), i64(gu.stride(0)),
+                                                  ptr(h), i64(h.stride(0)), i32(T), i32(F), i32(K), i32(1 if keep_gu else 0),
+                                                  stream_ptr()), "nv_gemm_swiglu_bf16"),
+           2.0 * T * 2 * F * K, 2.0 * (T * K + 2 * F * K + 3 * T * F))
+    return gu, h
+
+
+def gemm_dswiglu(dx, wd, gu, *, dgu=None):
+    """dgu = swiglu'(gu) ∘ (dx·Wd)  ([T,2F]) in ONE kernel: down-projection dgrad with the SwiGLU backward epilogue."""
+    _rowmajor(dx, "dx"); _rowmajor(wd, "wd"); _rowmajor(gu, "gu")
+    T, D = dx.shape
+    F = wd.shape[1]
+    if dgu is None:
+        dgu = torch.empty((T, 2 * F), dtype=bf16, device=dx.device)
+    lib = _lib.load()
+    _timed(lambda: check(lib.nv_gemm_dswiglu_bf16(ptr(dx), i64(dx.stride(0)), ptr(wd), i64(wd.stride(0)), ptr(gu), i64(gu.stride(0)),
+                                                   ptr(dgu), i64(dgu.stride(0)), i32(T), i32(F), i32(D), stream_ptr()),
+                         "nv_gemm_dswiglu_bf16"),
+           2.0 * T * F * D, 2.0 * (T * D + F * D + 4 * T * F))
+    return dgu
+
+
+def gemm_rope(x, w, pos, cos_t, sin_t, rope_cols, *, out=None):
+    """out = x·W^T with rotate-half RoPE applied to the first ``rope_cols`` columns in the epilogue."""
+    _rowmajor(x, "x"); _rowmajor(w, "w")
+    T, K = x.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty((T, N), dtype=bf16, device=x.device)
+    lib = _lib.load()
+    _timed(lambda: check(lib.nv_gemm_rope_bf16(ptr(x), i64(x.stride(0)), ptr(w), i64(w.stride(0)), ptr(out), i64(out.stride(0)),
+                                                ptr(pos), ptr(cos_t), ptr(sin_t), i32(T), i32(N), i32(K), i32(rope_cols),
+                                                stream_ptr()), "nv_gemm_rope_bf16"),
+           2.0 * T * N * K, 2.0 * (T * K + N * K + T * N))
+    return out

@@ -90,3 +90,29 @@ def test_gemm_skinny_m_weight_streaming(cuda_dev):
         ref = a.float() @ w.float().t()
         tol = 1.6e-2 * ref.abs() + 0.2
         assert bool(((out.float() - ref).abs() <= tol).all()) and bool(((auto.float() - ref).abs() <= tol).all())
+
+
+def test_fused_epilogues_are_bit_identical_to_unfused(cuda_dev):
+    """SwiGLU / SwiGLU-backward / RoPE epilogues of the CTA-pair GEMM vs GEMM followed by the row kernels."""
+    from navillm_b200 import ops
+    from navillm_b200.llama import LlamaDims, rope_tables
+    g = torch.Generator(device="cpu").manual_seed(21)
+    T, D, F, H = 1500, 1024, 1408, 8                                  # ragged T, F % 128 == 0, 8 heads of 128
+    x = torch.randn(T, D, generator=g).to(cuda_dev, torch.bfloat16)
+    wgu = (torch.randn(2 * F, D, generator=g) * 0.05).to(cuda_dev, torch.bfloat16)
+    gu_f, h_f = ops.gemm_swiglu(x, wgu)
+    gu_u = ops.gemm(x, wgu)
+    h_u = ops.swiglu_fwd(gu_u)
+    assert torch.equal(gu_f, gu_u) and torch.equal(h_f, h_u)
+    wd = (torch.randn(D, F, generator=g) * 0.05).to(cuda_dev, torch.bfloat16)
+    dx = torch.randn(T, D, generator=g).to(cuda_dev, torch.bfloat16)
+    dgu_f = ops.gemm_dswiglu(dx, wd, gu_u)
+    dgu_u = ops.swiglu_bwd(gu_u, ops.gemm(dx, wd, b_mn=True))
+    assert torch.equal(dgu_f, dgu_u)
+    wqkv = (torch.randn(3 * D, D, generator=g) * 0.05).to(cuda_dev, torch.bfloat16)
+    cos_t, sin_t = rope_tables(LlamaDims(hidden=D, n_heads=H, max_pos=2048), cuda_dev)
+    pos = torch.randint(0, 2048, (T,), generator=g).to(cuda_dev, torch.int32)
+    q_f = ops.gemm_rope(x, wqkv, pos, cos_t, sin_t, 2 * D)
+    q_u = ops.gemm(x, wqkv)
+    ops.rope_(q_u, pos, cos_t, sin_t, 2 * H)
+    assert torch.equal(q_f, q_u)
