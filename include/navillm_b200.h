@@ -68,7 +68,7 @@ int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
 int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
                 int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* dvec, void* dq, int64_t lddq,
                 void* dk, int64_t lddk, void* dv, int64_t lddv, const int* cu_seqlens, int B, int T, int H, int head_dim,
-                int total_blocks, float scale, void* stream);
+                int total_blocks, float scale, const int* rope_pos, const void* cos_t, const void* sin_t, void* stream);
 
 /* ---- row-wise LM kernels (csrc/lm_ops.cu) ---------------------------------------------------------------
  * LlamaRMSNorm, rotate-half RoPE, SwiGLU (HF LLaMA via models/modified_lm.py:112-116); embedding gather +

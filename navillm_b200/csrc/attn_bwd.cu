@@ -73,7 +73,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
                 const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
                 const float* __restrict__ lse, const float* __restrict__ Dvec, __nv_bfloat16* __restrict__ out0,
                 int64_t ld0, __nv_bfloat16* __restrict__ out1, int64_t ld1, const int* __restrict__ cu_seqlens, int B,
-                int T, float scale) {
+                int T, float scale, const int* __restrict__ rope_pos, const __nv_bfloat16* __restrict__ cos_t,
+                const __nv_bfloat16* __restrict__ sin_t) {
   using L = AttnBwdSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -214,7 +215,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t quarter = warp & 3;
     const uint32_t r = quarter * 32 + lane;
     const uint32_t lane_off = (quarter * 32) << 16;
-    const uint32_t c_begin = ((warp - 2) >> 2) * 64, c_end = c_begin + 64;
+    // the warp owns the 32-column chunks c0 and c0 + 64: a rotate-half RoPE pair (i, i + 64) stays in one thread,
+    // so the inverse rotation of dQ / dK can be applied in the epilogue (models/... HF apply_rotary_pos_emb backward)
+    const uint32_t c0 = ((warp - 2) >> 2) * 32;
     const float sl2 = scale * 1.4426950408889634f;
     for (uint32_t n = 0; n < n_it; ++n) {
       const uint32_t qb = (MODE == MODE_DKDV) ? (it_begin + n) : own;  // query block of this iteration
@@ -228,7 +231,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_wait(sdp_full, n & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (uint32_t c = c_begin; c < c_end; c += 32) {
+      for (uint32_t c = c0; c < 128; c += 64) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32(tmem_S + lane_off + c, sv);
         tmem_ld_32x32b_x32(tmem_dP + lane_off + c, dv);
@@ -273,21 +276,43 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       __nv_bfloat16* dst;
       if (MODE == MODE_DKDV) dst = (which == 0) ? (out1 + t * ld1 + head * 128) : (out0 + t * ld0 + head * 128);
       else dst = out0 + t * ld0 + head * 128;
-#pragma unroll 1
-      for (uint32_t c = c_begin; c < c_end; c += 32) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tm + lane_off + c, v);
-        tmem_ld_wait();
-        if (valid) {
+      const bool rope = rope_pos != nullptr && !(MODE == MODE_DKDV && which == 0);   // dQ and dK, never dV
+      uint32_t a[32], b[32];
+      tmem_ld_32x32b_x32(tm + lane_off + c0, a);
+      tmem_ld_32x32b_x32(tm + lane_off + c0 + 64, b);
+      tmem_ld_wait();
+      if (valid) {
+        const int p = rope ? rope_pos[t] : 0;
+        const __nv_bfloat16* cs = cos_t + (int64_t)p * 128;
+        const __nv_bfloat16* sn = sin_t + (int64_t)p * 128;
 #pragma unroll
-          for (uint32_t i = 0; i < 32; i += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[i + 0]), __uint_as_float(v[i + 1]));
-            o.y = pack_bf16x2(__uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
-            o.z = pack_bf16x2(__uint_as_float(v[i + 4]), __uint_as_float(v[i + 5]));
-            o.w = pack_bf16x2(__uint_as_float(v[i + 6]), __uint_as_float(v[i + 7]));
-            *reinterpret_cast<uint4*>(dst + c + i) = o;
+        for (uint32_t i = 0; i < 32; i += 8) {
+          uint4 o1, o2;
+          uint32_t* p1 = &o1.x; uint32_t* p2 = &o2.x;
+          uint4 c1 = make_uint4(0, 0, 0, 0), s1 = c1, c2 = c1, s2 = c1;
+          if (rope) {
+            c1 = *reinterpret_cast<const uint4*>(cs + c0 + i);      s1 = *reinterpret_cast<const uint4*>(sn + c0 + i);
+            c2 = *reinterpret_cast<const uint4*>(cs + 64 + c0 + i); s2 = *reinterpret_cast<const uint4*>(sn + 64 + c0 + i);
           }
+          const uint32_t* pc1 = &c1.x; const uint32_t* ps1 = &s1.x; const uint32_t* pc2 = &c2.x; const uint32_t* ps2 = &s2.x;
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) {
+            const uint32_t xa = pack_bf16x2(__uint_as_float(a[i + 2 * q]), __uint_as_float(a[i + 2 * q + 1]));
+            const uint32_t xb = pack_bf16x2(__uint_as_float(b[i + 2 * q]), __uint_as_float(b[i + 2 * q + 1]));
+            if (rope) {   // rotation by -theta on the bf16 gradient, same rounding points as rope_kernel(sign = -1)
+              const float y1l = bf16_round(bf16_lo(xa) * bf16_lo(pc1[q])) + bf16_round(bf16_lo(xb) * bf16_lo(ps1[q]));
+              const float y1h = bf16_round(bf16_hi(xa) * bf16_hi(pc1[q])) + bf16_round(bf16_hi(xb) * bf16_hi(ps1[q]));
+              const float y2l = bf16_round(bf16_lo(xb) * bf16_lo(pc2[q])) + bf16_round(-bf16_lo(xa) * bf16_lo(ps2[q]));
+              const float y2h = bf16_round(bf16_hi(xb) * bf16_hi(pc2[q])) + bf16_round(-bf16_hi(xa) * bf16_hi(ps2[q]));
+              p1[q] = pack_bf16x2(y1l, y1h);
+              p2[q] = pack_bf16x2(y2l, y2h);
+            } else {
+              p1[q] = xa;
+              p2[q] = xb;
+            }
+          }
+          *reinterpret_cast<uint4*>(dst + c0 + i) = o1;
+          *reinterpret_cast<uint4*>(dst + c0 + 64 + i) = o2;
         }
       }
     }
@@ -302,11 +327,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
 // Inputs: q,k,v (post-RoPE) and o, do as bf16 [T, H*128]-column views; lse [H,T] from the forward.
 // dvec: fp32 workspace [H, T].  Outputs dq, dk, dv: bf16 views with their own leading dimensions.
+// rope_pos/cos_t/sin_t (nullable): when given, dq and dk are rotated back by -theta[pos] in the epilogue, i.e. the
+// outputs are the gradients w.r.t. the PRE-RoPE q/k (fuses the backward of the rotary embedding).
 extern "C" int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                            const void* o, int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* dvec,
                            void* dq, int64_t lddq, void* dk, int64_t lddk, void* dv, int64_t lddv,
                            const int* cu_seqlens, int B, int T, int H, int head_dim, int total_blocks, float scale,
-                           void* stream_) {
+                           const int* rope_pos, const void* cos_t, const void* sin_t, void* stream_) {
   using namespace nv;
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   NV_REQUIRE(head_dim == 128, "nv_attn_bwd: head_dim must be 128 (got %d)", head_dim);
@@ -336,10 +363,12 @@ extern "C" int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
   dim3 grid(total_blocks, H);
   attn_bwd_kernel<MODE_DKDV><<<grid, AB_THREADS, AttnBwdSmem::DYN_BYTES, stream>>>(
       tq, tk, tv, tdo, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dk), lddk, reinterpret_cast<__nv_bfloat16*>(dv), lddv,
-      cu_seqlens, B, T, scale);
+      cu_seqlens, B, T, scale, rope_pos, reinterpret_cast<const __nv_bfloat16*>(cos_t),
+      reinterpret_cast<const __nv_bfloat16*>(sin_t));
   NV_LAUNCH_CHECK();
   attn_bwd_kernel<MODE_DQ><<<grid, AB_THREADS, AttnBwdSmem::DYN_BYTES, stream>>>(
-      tq, tk, tv, tdo, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dq), lddq, nullptr, 0, cu_seqlens, B, T, scale);
+      tq, tk, tv, tdo, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dq), lddq, nullptr, 0, cu_seqlens, B, T, scale, rope_pos,
+      reinterpret_cast<const __nv_bfloat16*>(cos_t), reinterpret_cast<const __nv_bfloat16*>(sin_t));
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -321,9 +321,9 @@ class LlamaCore:
                 full = torch.zeros_like(s.x)
                 ops.scatter_rows_(dxm, s.rows, full)
                 dxm = full
-            dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H)
+            # attention backward with the inverse rotary embedding of dq/dk fused into its epilogue
+            dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H, rope=(pos, self.cos, self.sin))
             del dao
-            ops.rope_(dqkv, pos, self.cos, self.sin, 2 * H, d.head_dim, backward=True)
             dxn = ops.gemm(dqkv, self.wqkv[l], b_mn=True)
             ops.gemm(dqkv, s.xn, a_mn=True, b_mn=True, out=self.gqkv[l], addend=add(self.gqkv[l]))
             del dqkv

@@ -242,8 +242,9 @@ def ce_fwd_bwd(logits, labels, special_ids, *, grad_scale=None):
 
 
 def attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Tensor, cu_seqlens: torch.Tensor, seqlens,
-             n_heads: int, *, dqkv: torch.Tensor | None = None, scale: float | None = None) -> torch.Tensor:
-    """Backward of attn_fwd (csrc/attn_bwd.cu): returns dqkv [T, 3*H*128] bf16 (dq | dk | dv)."""
+             n_heads: int, *, dqkv: torch.Tensor | None = None, scale: float | None = None, rope=None) -> torch.Tensor:
+    """Backward of attn_fwd (csrc/attn_bwd.cu): returns dqkv [T, 3*H*128] bf16 (dq | dk | dv).
+    rope = (pos int32 [T], cos_t, sin_t): also undo the rotary embedding in the epilogue (gradients w.r.t. pre-RoPE q/k)."""
     T, W = qkv.shape
     hd = 128
     HD = n_heads * hd
@@ -258,7 +259,9 @@ def attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Te
     check(_lib.load().nv_attn_bwd(ptr(q), i64(ld), ptr(k), i64(ld), ptr(v), i64(ld), ptr(o), i64(o.stride(0)), ptr(do),
                                   i64(do.stride(0)), ptr(lse), ptr(dvec), ptr(dq), i64(dqkv.stride(0)), ptr(dk),
                                   i64(dqkv.stride(0)), ptr(dv), i64(dqkv.stride(0)), ptr(cu_seqlens), i32(len(seqlens)),
-                                  i32(T), i32(n_heads), i32(hd), i32(_qblocks(seqlens)), f32(scale), stream_ptr()),
+                                  i32(T), i32(n_heads), i32(hd), i32(_qblocks(seqlens)), f32(scale),
+                                  ptr(rope[0] if rope else None), ptr(rope[1] if rope else None), ptr(rope[2] if rope else None),
+                                  stream_ptr()),
           "nv_attn_bwd")
     return dqkv
 

@@ -66,3 +66,22 @@ def test_attn_bwd(cuda_dev, seqlens, H):
         a, b = dqkv[:, sl].float(), qa.grad[:, sl]
         err = (a - b).abs().max().item()
         assert err <= 3e-2 * b.abs().max().item(), f"{name} err {err} vs max {b.abs().max().item()}"
+
+
+def test_attn_bwd_fused_inverse_rope_is_bit_identical(cuda_dev):
+    from navillm_b200 import ops
+    from navillm_b200.llama import LlamaDims, rope_tables
+    seqlens, H = [300, 129, 640], 2
+    T = sum(seqlens)
+    g = torch.Generator(device="cpu").manual_seed(77)
+    qkv = torch.randn(T, 3 * H * HD, generator=g).to(cuda_dev, torch.bfloat16)
+    do = torch.randn(T, H * HD, generator=g).to(cuda_dev, torch.bfloat16)
+    cu = torch.tensor([0] + list(torch.tensor(seqlens).cumsum(0)), dtype=torch.int32, device=cuda_dev)
+    pos = torch.randint(0, 1024, (T,), generator=g).to(cuda_dev, torch.int32)
+    cos_t, sin_t = rope_tables(LlamaDims(hidden=H * HD, n_heads=H, max_pos=1024), cuda_dev)
+    o, lse = ops.attn_fwd(qkv, cu, seqlens, H)
+    fused = ops.attn_bwd(qkv, o, do, lse, cu, seqlens, H, rope=(pos, cos_t, sin_t))
+    plain = ops.attn_bwd(qkv, o, do, lse, cu, seqlens, H)
+    ops.rope_(plain, pos, cos_t, sin_t, 2 * H, backward=True)
+    torch.cuda.synchronize()
+    assert torch.equal(fused, plain)
