@@ -1,4 +1,4 @@
-// navillm_b200 — causal self-attention backward on tcgen05 (packed variable-length rows).
+// navillm_b200 — causal self-attention backward on tcgen05 (packed variable-length rows), pipelined.
 //
 // Hand-written twin of attn_fwd.cu; replaces the autograd backward of HF LLaMA's eager attention
 // (reference: loss.backward() call sites tasks/agents/mp3d_agent.py:750-757, tasks/agents/llava.py:38-40
@@ -6,37 +6,32 @@
 //
 // With P = exp(S*scale - LSE), D_i = sum_d dO_id O_id, dS = P o (dP - D) * scale:
 //     dV = P^T dO      dK = dS^T Q      dQ = dS K
-// Two deterministic passes (no atomics) over the same code, selected by MODE:
-//   MODE_DKDV : CTA = (128-key block jb, head); loops over query blocks i >= jb; K_jb,V_jb resident,
-//               Q_i,dO_i streamed; accumulators dV,dK in TMEM.
-//   MODE_DQ   : CTA = (128-query block ib, head); loops over key blocks j <= ib; Q_ib,dO_ib resident,
-//               K_j,V_j streamed; accumulator dQ in TMEM.
-// Per iteration: S = Q K^T and dP = dO V^T (tcgen05, fp32 in TMEM) -> one thread per query row turns
-// them into P and dS (bf16, 128B-swizzled smem, [q rows x keys]) -> accumulate MMAs read them as
-// K-major (dQ) or MN-major (dV/dK: P^T, dS^T) operands.
-// TMEM: S [0,128) dP [128,256) acc0 [256,384) acc1 [384,512).  smem: 6 x 32 KB tiles = 192 KB.
+// Two deterministic passes (no atomics).  Both walk the partner dimension in 64-wide SUB-blocks so that the
+// score tiles are only 64 TMEM columns and can be double-buffered: the tensor pipe computes the scores of
+// sub-block n+1 while the compute warps turn sub-block n into P / dS and the accumulate MMAs of n run.
+//
+//   dq pass   CTA = (128-query block, head).  Q,dO resident; K_n,V_n [64 keys x 128] streamed (3 stages).
+//             S = Q K_n^T, dP = dO V_n^T  [128 q x 64 keys] -> dS (bf16, K-major A operand) -> dQ += dS K_n.
+//             TMEM: S[2] dP[2] (4 x 64 columns) + dQ (128).
+//   dkdv pass CTA = (128-key block, head).  K,V resident; Q_n,dO_n [64 queries x 128] streamed (2 stages).
+//             TRANSPOSED scores so that TMEM lanes are keys: S^T = K Q_n^T, dP^T = V dO_n^T [128 keys x 64 q]
+//             -> P^T, dS^T (bf16, K-major A operands) -> dV += P^T dO_n, dK += dS^T Q_n.
+//             TMEM: S^T[2] dP^T[2] (4 x 64) + dV (128) + dK (128) = 512 columns.
+// Roles: warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 compute (two warps per TMEM lane quarter, each owning
+// 32 of the 64 score columns; no row reductions are needed in the backward: LSE and D are precomputed).
+// The inverse rotary embedding of dQ / dK is applied in the epilogue (optional).
 #include "nv_common.cuh"
 #include "nv_host.h"
 
 namespace nv {
 
-constexpr uint32_t AB_TILE = 128 * 128 * 2;
-constexpr uint32_t AB_ATOM = 128 * 128;
-constexpr uint32_t AB_THREADS = 320;  // TMA warp, MMA warp, 8 compute warps (2 per TMEM lane quarter: column halves)
-constexpr int MODE_DKDV = 0, MODE_DQ = 1;
-
-struct AttnBwdSmem {
-  static constexpr uint32_t R0_OFF = 0;            // resident tile 0 (K | Q)
-  static constexpr uint32_t R1_OFF = 1 * AB_TILE;  // resident tile 1 (V | dO)
-  static constexpr uint32_t S0_OFF = 2 * AB_TILE;  // streamed tile 0 (Q_i | K_j)
-  static constexpr uint32_t S1_OFF = 3 * AB_TILE;  // streamed tile 1 (dO_i | V_j)
-  static constexpr uint32_t P_OFF = 4 * AB_TILE;
-  static constexpr uint32_t DS_OFF = 5 * AB_TILE;
-  static constexpr uint32_t BAR_OFF = 6 * AB_TILE;
-  static constexpr uint32_t NUM_BARS = 5;  // res_full, ld_full, sdp_full, pds_ready, acc_done
-  static constexpr uint32_t TOTAL = BAR_OFF + NUM_BARS * 8 + 16;
-  static constexpr uint32_t DYN_BYTES = TOTAL + 1024;
-};
+constexpr uint32_t AB_THREADS = 320;
+constexpr uint32_t AB_T128 = 128 * 128 * 2;  // [128 rows x 128 hd] bf16 = two 16 KB swizzle atoms (hd halves)
+constexpr uint32_t AB_A128 = 128 * 128;      // one atom of a 128-row tile
+constexpr uint32_t AB_T64 = 64 * 128 * 2;    // [64 rows x 128 hd] bf16 = two 8 KB atoms
+constexpr uint32_t AB_A64 = 64 * 128;        // one atom of a 64-row tile
+constexpr uint32_t AB_PS = 128 * 64 * 2;     // [128 rows x 64 cols] bf16 = one 16 KB atom (P / dS operands)
+constexpr float LOG2E = 1.4426950408889634f;
 
 __device__ __forceinline__ bool locate_block_bwd(const int* __restrict__ cu, int B, uint32_t blk, int& seq_start,
                                                  int& seq_len, uint32_t& idx) {
@@ -67,56 +62,117 @@ __global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, int64_
   if (lane == 0) D[(int64_t)h * T + t] = s;
 }
 
-template <int MODE>
+// Load a [rows x 128 hd] tile as 64-row x 64-col boxes into the two-atom layout (atom = hd half).
+template <uint32_t ROWS>
+__device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* m, uint64_t* bar, int32_t col, int32_t row) {
+  constexpr uint32_t ATOM = ROWS * 128;
+#pragma unroll
+  for (uint32_t a = 0; a < 2; ++a)
+#pragma unroll
+    for (uint32_t r = 0; r < ROWS / 64; ++r)
+      tma_load_2d(dst + a * ATOM + r * (64 * 128), m, bar, col + a * 64, row + r * 64);
+}
+
+// Epilogue shared by both passes: accumulator rows -> bf16 (-> inverse RoPE) -> HBM.  The warp owns the 32-column
+// chunks c0 and c0 + 64, i.e. complete rotate-half pairs.
+__device__ __forceinline__ void store_acc_rows(uint32_t tm, uint32_t lane_off, uint32_t c0, bool valid,
+                                               __nv_bfloat16* dst, bool rope, int pos,
+                                               const __nv_bfloat16* __restrict__ cos_t,
+                                               const __nv_bfloat16* __restrict__ sin_t) {
+  uint32_t a[32], b[32];
+  tmem_ld_32x32b_x32(tm + lane_off + c0, a);
+  tmem_ld_32x32b_x32(tm + lane_off + c0 + 64, b);
+  tmem_ld_wait();
+  if (!valid) return;
+  const __nv_bfloat16* cs = cos_t + (int64_t)pos * 128;
+  const __nv_bfloat16* sn = sin_t + (int64_t)pos * 128;
+#pragma unroll
+  for (uint32_t i = 0; i < 32; i += 8) {
+    uint4 o1, o2;
+    uint32_t* p1 = &o1.x; uint32_t* p2 = &o2.x;
+    uint4 c1 = make_uint4(0, 0, 0, 0), s1 = c1, c2 = c1, s2 = c1;
+    if (rope) {
+      c1 = *reinterpret_cast<const uint4*>(cs + c0 + i);      s1 = *reinterpret_cast<const uint4*>(sn + c0 + i);
+      c2 = *reinterpret_cast<const uint4*>(cs + 64 + c0 + i); s2 = *reinterpret_cast<const uint4*>(sn + 64 + c0 + i);
+    }
+    const uint32_t* pc1 = &c1.x; const uint32_t* ps1 = &s1.x; const uint32_t* pc2 = &c2.x; const uint32_t* ps2 = &s2.x;
+#pragma unroll
+    for (uint32_t q = 0; q < 4; ++q) {
+      const uint32_t xa = pack_bf16x2(__uint_as_float(a[i + 2 * q]), __uint_as_float(a[i + 2 * q + 1]));
+      const uint32_t xb = pack_bf16x2(__uint_as_float(b[i + 2 * q]), __uint_as_float(b[i + 2 * q + 1]));
+      if (rope) {   // rotation by -theta on the bf16 gradient, same rounding points as rope_kernel(sign = -1)
+        const float y1l = bf16_round(bf16_lo(xa) * bf16_lo(pc1[q])) + bf16_round(bf16_lo(xb) * bf16_lo(ps1[q]));
+        const float y1h = bf16_round(bf16_hi(xa) * bf16_hi(pc1[q])) + bf16_round(bf16_hi(xb) * bf16_hi(ps1[q]));
+        const float y2l = bf16_round(bf16_lo(xb) * bf16_lo(pc2[q])) + bf16_round(-bf16_lo(xa) * bf16_lo(ps2[q]));
+        const float y2h = bf16_round(bf16_hi(xb) * bf16_hi(pc2[q])) + bf16_round(-bf16_hi(xa) * bf16_hi(ps2[q]));
+        p1[q] = pack_bf16x2(y1l, y1h);
+        p2[q] = pack_bf16x2(y2l, y2h);
+      } else {
+        p1[q] = xa;
+        p2[q] = xb;
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + c0 + i) = o1;
+    *reinterpret_cast<uint4*>(dst + c0 + 64 + i) = o2;
+  }
+}
+
+// ======================================================================================================
+// dq pass
+// ======================================================================================================
+struct DqSmem {
+  static constexpr uint32_t NST = 3;
+  static constexpr uint32_t Q_OFF = 0, DO_OFF = AB_T128;
+  static constexpr uint32_t KV_OFF = 2 * AB_T128;                 // NST x (K 16K | V 16K)
+  static constexpr uint32_t DS_OFF = KV_OFF + NST * 2 * AB_T64;   // 2 x 16K
+  static constexpr uint32_t BAR_OFF = DS_OFF + 2 * AB_PS;
+  // res_full, kv_full[3], kv_empty[3], sdp_full[2], sdp_empty[2], ds_full[2], ds_empty[2], done
+  static constexpr uint32_t NUM_BARS = 16;
+  static constexpr uint32_t DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
 __global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
-                const float* __restrict__ lse, const float* __restrict__ Dvec, __nv_bfloat16* __restrict__ out0,
-                int64_t ld0, __nv_bfloat16* __restrict__ out1, int64_t ld1, const int* __restrict__ cu_seqlens, int B,
-                int T, float scale, const int* __restrict__ rope_pos, const __nv_bfloat16* __restrict__ cos_t,
-                const __nv_bfloat16* __restrict__ sin_t) {
-  using L = AttnBwdSmem;
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                   const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                   const float* __restrict__ lse, const float* __restrict__ Dvec, __nv_bfloat16* __restrict__ dq,
+                   int64_t lddq, const int* __restrict__ cu_seqlens, int B, int T, float scale,
+                   const int* __restrict__ rope_pos, const __nv_bfloat16* __restrict__ cos_t,
+                   const __nv_bfloat16* __restrict__ sin_t) {
+  using L = DqSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sR0 = smem + L::R0_OFF;
-  uint8_t* sR1 = smem + L::R1_OFF;
-  uint8_t* sS0 = smem + L::S0_OFF;
-  uint8_t* sS1 = smem + L::S1_OFF;
-  uint8_t* sP = smem + L::P_OFF;
+  uint8_t* sQ = smem + L::Q_OFF;
+  uint8_t* sdO = smem + L::DO_OFF;
+  uint8_t* sKV = smem + L::KV_OFF;
   uint8_t* sDS = smem + L::DS_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* res_full = bars + 0;
-  uint64_t* ld_full = bars + 1;
-  uint64_t* sdp_full = bars + 2;
-  uint64_t* pds_ready = bars + 3;
-  uint64_t* acc_done = bars + 4;
+  uint64_t* kv_full = bars + 1;     // [3]
+  uint64_t* kv_empty = bars + 4;    // [3]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* sdp_empty = bars + 9;   // [2]
+  uint64_t* ds_full = bars + 11;    // [2]
+  uint64_t* ds_empty = bars + 13;   // [2]
+  uint64_t* done = bars + 15;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
   int seq_start = 0, seq_len = 0;
   uint32_t own = 0;
-  const uint32_t flat = (MODE == MODE_DQ) ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x;  // heavy blocks first
-  if (!locate_block_bwd(cu_seqlens, B, flat, seq_start, seq_len, own)) return;
-  const uint32_t nblk = (seq_len + 127) / 128;
-  // partner-block range: DKDV -> query blocks own..nblk-1 ; DQ -> key blocks 0..own
-  const uint32_t it_begin = (MODE == MODE_DKDV) ? own : 0;
-  const uint32_t it_end = (MODE == MODE_DKDV) ? nblk : own + 1;
-  const uint32_t n_it = it_end - it_begin;
-
-  // Smem views by role.  Q/dO/K/V tiles are all [128 rows x 128 hd] as two 64-wide swizzle atoms.
-  uint8_t* sQ = (MODE == MODE_DKDV) ? sS0 : sR0;
-  uint8_t* sdO = (MODE == MODE_DKDV) ? sS1 : sR1;
-  uint8_t* sK = (MODE == MODE_DKDV) ? sR0 : sS0;
-  uint8_t* sV = (MODE == MODE_DKDV) ? sR1 : sS1;
+  if (!locate_block_bwd(cu_seqlens, B, gridDim.x - 1 - blockIdx.x, seq_start, seq_len, own)) return;  // heavy first
+  // 64-key sub-blocks 0 .. n_sub-1 cover keys [0, min((own+1)*128, len))
+  const uint32_t n_sub = min(2 * own + 2, (uint32_t)(seq_len + 63) / 64);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
     mbar_init(res_full, 1);
-    mbar_init(ld_full, 1);
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_ready, 256);
-    mbar_init(acc_done, 1);
+    for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
+      mbar_init(&ds_full[i], 8);  mbar_init(&ds_empty[i], 1);
+    }
+    mbar_init(done, 1);
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
@@ -124,198 +180,336 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_A0 = tmem_base + 256, tmem_A1 = tmem_base + 384;
+  const uint32_t tmem_dQ = tmem_base + 256;
 
   if (warp == 0) {
     if (lane == 0) {
       const int32_t col = head * 128;
-      const int32_t own_row = seq_start + own * 128;
-      mbar_arrive_expect_tx(res_full, 2 * AB_TILE);
-      if (MODE == MODE_DKDV) {
-        tma_load_2d(sR0, &tmap_k, res_full, col, own_row);
-        tma_load_2d(sR0 + AB_ATOM, &tmap_k, res_full, col + 64, own_row);
-        tma_load_2d(sR1, &tmap_v, res_full, col, own_row);
-        tma_load_2d(sR1 + AB_ATOM, &tmap_v, res_full, col + 64, own_row);
-      } else {
-        tma_load_2d(sR0, &tmap_q, res_full, col, own_row);
-        tma_load_2d(sR0 + AB_ATOM, &tmap_q, res_full, col + 64, own_row);
-        tma_load_2d(sR1, &tmap_do, res_full, col, own_row);
-        tma_load_2d(sR1 + AB_ATOM, &tmap_do, res_full, col + 64, own_row);
-      }
-      for (uint32_t n = 0; n < n_it; ++n) {
-        if (n > 0) mbar_wait(acc_done, (n - 1) & 1);  // previous iteration's MMAs finished reading the tiles
-        const int32_t row = seq_start + (it_begin + n) * 128;
-        mbar_arrive_expect_tx(ld_full, 2 * AB_TILE);
-        const CUtensorMap* m0 = (MODE == MODE_DKDV) ? &tmap_q : &tmap_k;
-        const CUtensorMap* m1 = (MODE == MODE_DKDV) ? &tmap_do : &tmap_v;
-        tma_load_2d(sS0, m0, ld_full, col, row);
-        tma_load_2d(sS0 + AB_ATOM, m0, ld_full, col + 64, row);
-        tma_load_2d(sS1, m1, ld_full, col, row);
-        tma_load_2d(sS1 + AB_ATOM, m1, ld_full, col + 64, row);
+      mbar_arrive_expect_tx(res_full, 2 * AB_T128);
+      load_tile<128>(sQ, &tmap_q, res_full, col, seq_start + own * 128);
+      load_tile<128>(sdO, &tmap_do, res_full, col, seq_start + own * 128);
+      for (uint32_t n = 0; n < n_sub; ++n) {
+        const uint32_t st = n % 3, use = n / 3;
+        mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+        mbar_arrive_expect_tx(&kv_full[st], 2 * AB_T64);
+        load_tile<64>(sKV + st * 2 * AB_T64, &tmap_k, &kv_full[st], col, seq_start + n * 64);
+        load_tile<64>(sKV + st * 2 * AB_T64 + AB_T64, &tmap_v, &kv_full[st], col, seq_start + n * 64);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc_kk = umma_idesc_bf16(128, 128, 0, 0);
-      constexpr uint32_t idesc_mm = umma_idesc_bf16(128, 128, 1, 1);
-      constexpr uint32_t idesc_km = umma_idesc_bf16(128, 128, 0, 1);
-      // loop-invariant operand descriptors (the issuing thread is the serial resource: keep its loop short)
-      uint64_t q_k[2], k_k[2], o_k[2], v_k[2], ds_k[2];
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // [128 q] x [64 keys], both K-major over hd
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);  // dS (K-major over keys) x K_n (MN-major: hd contiguous)
+      uint64_t q_k[2], o_k[2], ds_k[2];
 #pragma unroll
       for (uint32_t ka = 0; ka < 2; ++ka) {
-        q_k[ka] = umma_smem_desc_sw128(smem_u32(sQ + ka * AB_ATOM), 0, 1024);     // K-major over hd
-        k_k[ka] = umma_smem_desc_sw128(smem_u32(sK + ka * AB_ATOM), 0, 1024);
-        o_k[ka] = umma_smem_desc_sw128(smem_u32(sdO + ka * AB_ATOM), 0, 1024);
-        v_k[ka] = umma_smem_desc_sw128(smem_u32(sV + ka * AB_ATOM), 0, 1024);
-        ds_k[ka] = umma_smem_desc_sw128(smem_u32(sDS + ka * AB_ATOM), 0, 1024);   // K-major over keys
+        q_k[ka] = umma_smem_desc_sw128(smem_u32(sQ + ka * AB_A128), 0, 1024);
+        o_k[ka] = umma_smem_desc_sw128(smem_u32(sdO + ka * AB_A128), 0, 1024);
       }
-      // MN-major views (rows = contraction index, 64-wide MN atoms AB_ATOM bytes apart); k-step = 16 rows = 2048 B
-      const uint64_t p_m = umma_smem_desc_sw128(smem_u32(sP), AB_ATOM, 1024);
-      const uint64_t ds_m = umma_smem_desc_sw128(smem_u32(sDS), AB_ATOM, 1024);
-      const uint64_t o_m = umma_smem_desc_sw128(smem_u32(sdO), AB_ATOM, 1024);
-      const uint64_t q_m = umma_smem_desc_sw128(smem_u32(sQ), AB_ATOM, 1024);
-      const uint64_t k_m = umma_smem_desc_sw128(smem_u32(sK), AB_ATOM, 1024);
-      mbar_wait(res_full, 0);
-      for (uint32_t n = 0; n < n_it; ++n) {
-        mbar_wait(ld_full, n & 1);
+#pragma unroll
+      for (uint32_t b = 0; b < 2; ++b) ds_k[b] = umma_smem_desc_sw128(smem_u32(sDS + b * AB_PS), 0, 1024);
+      auto issue_sdp = [&](uint32_t n) {
+        const uint32_t st = n % 3, b = n & 1;
+        mbar_wait(&kv_full[st], (n / 3) & 1);
+        mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
-        // S = Q K^T ; dP = dO V^T   (both operands K-major over hd: 2 atoms x 4 k-steps)
+        const uint32_t kbase = smem_u32(sKV + st * 2 * AB_T64), vbase = kbase + AB_T64;
 #pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka)
+        for (uint32_t ka = 0; ka < 2; ++ka) {
+          const uint64_t kd = umma_smem_desc_sw128(kbase + ka * AB_A64, 0, 1024);
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_S, q_k[ka] + ks * 2, k_k[ka] + ks * 2, idesc_kk, (ka | ks) ? 1u : 0u);
-#pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka)
-#pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dP, o_k[ka] + ks * 2, v_k[ka] + ks * 2, idesc_kk, (ka | ks) ? 1u : 0u);
-        umma_commit(sdp_full);
-        mbar_wait(pds_ready, n & 1);
-        tc_fence_after();
-        if (MODE == MODE_DKDV) {
-          // dV += P^T dO ; dK += dS^T Q : contraction over the 128 query rows (8 k-steps of 16 rows)
-#pragma unroll
-          for (uint32_t ks = 0; ks < 8; ++ks) umma_f16_ss(tmem_A0, p_m + ks * 128, o_m + ks * 128, idesc_mm, (n | ks) ? 1u : 0u);
-#pragma unroll
-          for (uint32_t ks = 0; ks < 8; ++ks) umma_f16_ss(tmem_A1, ds_m + ks * 128, q_m + ks * 128, idesc_mm, (n | ks) ? 1u : 0u);
-        } else {
-          // dQ += dS K : A = dS K-major over keys (2 atoms x 4 k-steps), B = K MN-major (hd contiguous)
-#pragma unroll
-          for (uint32_t ka = 0; ka < 2; ++ka)
-#pragma unroll
-            for (uint32_t ks = 0; ks < 4; ++ks)
-              umma_f16_ss(tmem_A0, ds_k[ka] + ks * 2, k_m + ((ka * 64 + ks * 16) * 128 >> 4), idesc_km, (n | ka | ks) ? 1u : 0u);
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_f16_ss(tmem_base + b * 64, q_k[ka] + ks * 2, kd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
         }
-        umma_commit(acc_done);
+#pragma unroll
+        for (uint32_t ka = 0; ka < 2; ++ka) {
+          const uint64_t vd = umma_smem_desc_sw128(vbase + ka * AB_A64, 0, 1024);
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_f16_ss(tmem_base + 128 + b * 64, o_k[ka] + ks * 2, vd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
+        }
+        umma_commit(&sdp_full[b]);
+      };
+      mbar_wait(res_full, 0);
+      issue_sdp(0);
+      for (uint32_t n = 0; n < n_sub; ++n) {
+        if (n + 1 < n_sub) issue_sdp(n + 1);
+        const uint32_t st = n % 3, b = n & 1;
+        mbar_wait(&ds_full[b], (n >> 1) & 1);
+        tc_fence_after();
+        // dQ += dS K_n : contraction over the 64 keys (4 k-steps); B rows = keys, 64-wide hd atoms AB_A64 apart
+        const uint64_t km = umma_smem_desc_sw128(smem_u32(sKV + st * 2 * AB_T64), AB_A64, 1024);
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks)
+          umma_f16_ss(tmem_dQ, ds_k[b] + ks * 2, km + ks * 128, idesc_dq, (n | ks) ? 1u : 0u);
+        umma_commit(&ds_empty[b]);
+        umma_commit(&kv_empty[st]);
       }
+      umma_commit(done);
     }
   } else {
-    // Two warps share each TMEM lane quarter (a warp may touch lanes 32*(warp%4)..+31 only) and split the 128
-    // key columns in halves: no row reductions are needed in the backward (LSE and D are precomputed), so the
-    // element-wise phase parallelises over columns and every SMSP holds two compute warps to hide latencies.
-    const uint32_t quarter = warp & 3;
+    const uint32_t quarter = warp & 3, half = (warp - 2) >> 2;
     const uint32_t r = quarter * 32 + lane;
     const uint32_t lane_off = (quarter * 32) << 16;
-    // the warp owns the 32-column chunks c0 and c0 + 64: a rotate-half RoPE pair (i, i + 64) stays in one thread,
-    // so the inverse rotation of dQ / dK can be applied in the epilogue (models/... HF apply_rotary_pos_emb backward)
-    const uint32_t c0 = ((warp - 2) >> 2) * 32;
-    const float sl2 = scale * 1.4426950408889634f;
-    for (uint32_t n = 0; n < n_it; ++n) {
-      const uint32_t qb = (MODE == MODE_DKDV) ? (it_begin + n) : own;  // query block of this iteration
-      const uint32_t kb = (MODE == MODE_DKDV) ? own : (it_begin + n);  // key block
-      const uint32_t qi = qb * 128 + r;
-      const bool row_valid = qi < (uint32_t)seq_len;
-      const int64_t t = (int64_t)seq_start + qi;
-      const float lse_r = row_valid ? lse[(int64_t)head * T + t] * 1.4426950408889634f : 0.f;
-      const float d_r = row_valid ? Dvec[(int64_t)head * T + t] : 0.f;
-      const bool diag = (qb == kb);
-      mbar_wait(sdp_full, n & 1);
+    const float sl2 = scale * LOG2E;
+    const uint32_t qi = own * 128 + r;
+    const bool row_valid = qi < (uint32_t)seq_len;
+    const int64_t tok = (int64_t)seq_start + qi;
+    // an invalid row gets LSE = +inf -> p = exp2(-inf) = 0 without a branch
+    const float lse_r = row_valid ? lse[(int64_t)head * T + tok] * LOG2E : INFINITY;
+    const float d_r = row_valid ? Dvec[(int64_t)head * T + tok] : 0.f;
+    for (uint32_t n = 0; n < n_sub; ++n) {
+      const uint32_t b = n & 1;
+      mbar_wait(&sdp_full[b], (n >> 1) & 1);
       tc_fence_after();
-#pragma unroll 1
-      for (uint32_t c = c0; c < 128; c += 64) {
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_off + c, sv);
-        tmem_ld_32x32b_x32(tmem_dP + lane_off + c, dv);
-        tmem_ld_wait();
-        uint32_t pp[16], dd[16];
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32b_x32(tmem_base + b * 64 + lane_off + half * 32, sv);
+      tmem_ld_32x32b_x32(tmem_base + 128 + b * 64 + lane_off + half * 32, dv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sdp_empty[b]);           // score buffers may be overwritten by sub-block n+2
+      const bool diag = (n >= 2 * own);                     // sub-blocks that touch the diagonal 128x128 block
+      const uint32_t key0 = n * 64 + half * 32;             // first key of this thread's 32 columns
+      uint32_t dd[16];
 #pragma unroll
-        for (uint32_t i = 0; i < 32; i += 2) {
-          float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - lse_r);
-          float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse_r);
-          if (!row_valid || (diag && c + i > r)) p0 = 0.f;
-          if (!row_valid || (diag && c + i + 1 > r)) p1 = 0.f;
-          const float g0 = p0 * (__uint_as_float(dv[i]) - d_r) * scale;
-          const float g1 = p1 * (__uint_as_float(dv[i + 1]) - d_r) * scale;
-          pp[i >> 1] = pack_bf16x2(p0, p1);
-          dd[i >> 1] = pack_bf16x2(g0, g1);
+      for (uint32_t i = 0; i < 32; i += 2) {
+        float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - lse_r);
+        float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse_r);
+        if (diag) {
+          if (key0 + i > qi) p0 = 0.f;
+          if (key0 + i + 1 > qi) p1 = 0.f;
         }
-        const uint32_t atom_off = (c >> 6) * AB_ATOM;
-        const uint32_t chunk0 = (c & 63) >> 3;
+        dd[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[i]) - d_r) * scale, p1 * (__uint_as_float(dv[i + 1]) - d_r) * scale);
+      }
+      mbar_wait(&ds_empty[b], ((n >> 1) & 1) ^ 1);         // dQ MMA of sub-block n-2 has consumed this buffer
+      uint8_t* dsb = sDS + b * AB_PS;
 #pragma unroll
-        for (uint32_t q = 0; q < 4; ++q) {
-          const uint32_t off = atom_off + sw128_offset(r, chunk0 + q);
-          if (MODE == MODE_DKDV)
-            *reinterpret_cast<uint4*>(sP + off) = make_uint4(pp[q * 4], pp[q * 4 + 1], pp[q * 4 + 2], pp[q * 4 + 3]);
-          *reinterpret_cast<uint4*>(sDS + off) = make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
+      for (uint32_t q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4*>(dsb + sw128_offset(r, half * 4 + q)) = make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[b]);
+    }
+    mbar_wait(done, 0);
+    tc_fence_after();
+    store_acc_rows(tmem_dQ, lane_off, half * 32, row_valid, dq + tok * lddq + head * 128, rope_pos != nullptr,
+                   (rope_pos != nullptr && row_valid) ? rope_pos[tok] : 0, cos_t, sin_t);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+}
+
+// ======================================================================================================
+// dk/dv pass (transposed scores: TMEM lanes = keys)
+// ======================================================================================================
+struct DkvSmem {
+  static constexpr uint32_t NST = 2;
+  static constexpr uint32_t K_OFF = 0, V_OFF = AB_T128;
+  static constexpr uint32_t QO_OFF = 2 * AB_T128;                 // NST x (Q 16K | dO 16K)
+  static constexpr uint32_t PT_OFF = QO_OFF + NST * 2 * AB_T64;   // 2 x 16K
+  static constexpr uint32_t DST_OFF = PT_OFF + 2 * AB_PS;         // 2 x 16K
+  static constexpr uint32_t BAR_OFF = DST_OFF + 2 * AB_PS;
+  // res_full, qo_full[2], qo_empty[2], sdp_full[2], sdp_empty[2], pds_full[2], pds_empty[2], done
+  static constexpr uint32_t NUM_BARS = 14;
+  static constexpr uint32_t DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
+};
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
+                    const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+                    const float* __restrict__ lse, const float* __restrict__ Dvec, __nv_bfloat16* __restrict__ dk,
+                    int64_t lddk, __nv_bfloat16* __restrict__ dv, int64_t lddv, const int* __restrict__ cu_seqlens,
+                    int B, int T, float scale, const int* __restrict__ rope_pos,
+                    const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t) {
+  using L = DkvSmem;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem + L::K_OFF;
+  uint8_t* sV = smem + L::V_OFF;
+  uint8_t* sQO = smem + L::QO_OFF;
+  uint8_t* sPT = smem + L::PT_OFF;
+  uint8_t* sDST = smem + L::DST_OFF;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+  uint64_t* res_full = bars + 0;
+  uint64_t* qo_full = bars + 1;     // [2]
+  uint64_t* qo_empty = bars + 3;    // [2]
+  uint64_t* sdp_full = bars + 5;    // [2]
+  uint64_t* sdp_empty = bars + 7;   // [2]
+  uint64_t* pds_full = bars + 9;    // [2]
+  uint64_t* pds_empty = bars + 11;  // [2]
+  uint64_t* done = bars + 13;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
+  __shared__ float s_stats[8][2][32];   // per compute warp: LSE*log2e and D of its 32 query columns
+
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t head = blockIdx.y;
+  int seq_start = 0, seq_len = 0;
+  uint32_t own = 0;
+  if (!locate_block_bwd(cu_seqlens, B, blockIdx.x, seq_start, seq_len, own)) return;   // early key blocks are the heavy ones
+  // 64-query sub-blocks first .. n_qsub-1 can see keys of this block (causal): q >= own*128
+  const uint32_t first = 2 * own, n_qsub = (uint32_t)(seq_len + 63) / 64;
+  const uint32_t n_it = n_qsub - first;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+    mbar_init(res_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qo_full[i], 1);  mbar_init(&qo_empty[i], 1);
+      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
+      mbar_init(&pds_full[i], 8); mbar_init(&pds_empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_ptr_smem, 512); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 384;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const int32_t col = head * 128;
+      mbar_arrive_expect_tx(res_full, 2 * AB_T128);
+      load_tile<128>(sK, &tmap_k, res_full, col, seq_start + own * 128);
+      load_tile<128>(sV, &tmap_v, res_full, col, seq_start + own * 128);
+      for (uint32_t n = 0; n < n_it; ++n) {
+        const uint32_t st = n & 1, use = n >> 1;
+        mbar_wait(&qo_empty[st], (use & 1) ^ 1);
+        mbar_arrive_expect_tx(&qo_full[st], 2 * AB_T64);
+        load_tile<64>(sQO + st * 2 * AB_T64, &tmap_q, &qo_full[st], col, seq_start + (first + n) * 64);
+        load_tile<64>(sQO + st * 2 * AB_T64 + AB_T64, &tmap_do, &qo_full[st], col, seq_start + (first + n) * 64);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);     // [128 keys] x [64 q], both K-major over hd
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);  // P^T/dS^T (K-major over q) x dO_n/Q_n (MN-major)
+      uint64_t k_k[2], v_k[2], pt_k[2], dst_k[2];
+#pragma unroll
+      for (uint32_t ka = 0; ka < 2; ++ka) {
+        k_k[ka] = umma_smem_desc_sw128(smem_u32(sK + ka * AB_A128), 0, 1024);
+        v_k[ka] = umma_smem_desc_sw128(smem_u32(sV + ka * AB_A128), 0, 1024);
+      }
+#pragma unroll
+      for (uint32_t b = 0; b < 2; ++b) {
+        pt_k[b] = umma_smem_desc_sw128(smem_u32(sPT + b * AB_PS), 0, 1024);
+        dst_k[b] = umma_smem_desc_sw128(smem_u32(sDST + b * AB_PS), 0, 1024);
+      }
+      auto issue_sdp = [&](uint32_t n) {
+        const uint32_t st = n & 1, b = n & 1;
+        mbar_wait(&qo_full[st], (n >> 1) & 1);
+        mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t qbase = smem_u32(sQO + st * 2 * AB_T64), obase = qbase + AB_T64;
+#pragma unroll
+        for (uint32_t ka = 0; ka < 2; ++ka) {
+          const uint64_t qd = umma_smem_desc_sw128(qbase + ka * AB_A64, 0, 1024);
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_f16_ss(tmem_base + b * 64, k_k[ka] + ks * 2, qd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
         }
+#pragma unroll
+        for (uint32_t ka = 0; ka < 2; ++ka) {
+          const uint64_t od = umma_smem_desc_sw128(obase + ka * AB_A64, 0, 1024);
+#pragma unroll
+          for (uint32_t ks = 0; ks < 4; ++ks)
+            umma_f16_ss(tmem_base + 128 + b * 64, v_k[ka] + ks * 2, od + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
+        }
+        umma_commit(&sdp_full[b]);
+      };
+      mbar_wait(res_full, 0);
+      issue_sdp(0);
+      for (uint32_t n = 0; n < n_it; ++n) {
+        // NB: with 2 stream stages, Q_{n+1}/dO_{n+1} land in the stage that sub-block n-1 released
+        if (n + 1 < n_it) issue_sdp(n + 1);
+        const uint32_t st = n & 1, b = n & 1;
+        mbar_wait(&pds_full[b], (n >> 1) & 1);
+        tc_fence_after();
+        // contraction over the 64 queries (4 k-steps); B rows = queries, 64-wide hd atoms AB_A64 apart
+        const uint64_t om = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64 + AB_T64), AB_A64, 1024);
+        const uint64_t qm = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64), AB_A64, 1024);
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dV, pt_k[b] + ks * 2, om + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
+#pragma unroll
+        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dK, dst_k[b] + ks * 2, qm + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
+        umma_commit(&pds_empty[b]);
+        umma_commit(&qo_empty[st]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    const uint32_t cw = warp - 2;
+    const uint32_t quarter = warp & 3, half = cw >> 2;
+    const uint32_t r = quarter * 32 + lane;                 // key row of this thread
+    const uint32_t lane_off = (quarter * 32) << 16;
+    const float sl2 = scale * LOG2E;
+    const uint32_t kj = own * 128 + r;                      // key index inside the sequence
+    float* st_l = s_stats[cw][0];
+    float* st_d = s_stats[cw][1];
+    for (uint32_t n = 0; n < n_it; ++n) {
+      const uint32_t b = n & 1;
+      // statistics of this warp's 32 query columns: coalesced load, shared inside the warp through smem
+      const uint32_t q0 = (first + n) * 64 + half * 32;     // first query of the 32 columns
+      {
+        const uint32_t qi = q0 + lane;
+        const bool ok = qi < (uint32_t)seq_len;
+        const int64_t tq = (int64_t)seq_start + qi;
+        __syncwarp();
+        st_l[lane] = ok ? lse[(int64_t)head * T + tq] * LOG2E : INFINITY;   // +inf -> p = 0 for rows past the sequence
+        st_d[lane] = ok ? Dvec[(int64_t)head * T + tq] : 0.f;
+        __syncwarp();
+      }
+      mbar_wait(&sdp_full[b], (n >> 1) & 1);
+      tc_fence_after();
+      uint32_t sv[32], dv[32];
+      tmem_ld_32x32b_x32(tmem_base + b * 64 + lane_off + half * 32, sv);
+      tmem_ld_32x32b_x32(tmem_base + 128 + b * 64 + lane_off + half * 32, dv);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sdp_empty[b]);
+      const bool diag = (first + n) < 2 * own + 2;          // query sub-blocks inside the diagonal 128x128 block
+      uint32_t pp[16], dd[16];
+#pragma unroll
+      for (uint32_t i = 0; i < 32; i += 2) {
+        const float2 l2 = *reinterpret_cast<const float2*>(st_l + i);
+        const float2 d2 = *reinterpret_cast<const float2*>(st_d + i);
+        float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - l2.x);
+        float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - l2.y);
+        if (diag) {                                         // causal: a query sees keys <= itself
+          if (q0 + i < kj) p0 = 0.f;
+          if (q0 + i + 1 < kj) p1 = 0.f;
+        }
+        pp[i >> 1] = pack_bf16x2(p0, p1);
+        dd[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[i]) - d2.x) * scale, p1 * (__uint_as_float(dv[i + 1]) - d2.y) * scale);
+      }
+      mbar_wait(&pds_empty[b], ((n >> 1) & 1) ^ 1);
+      uint8_t* ptb = sPT + b * AB_PS;
+      uint8_t* dsb = sDST + b * AB_PS;
+#pragma unroll
+      for (uint32_t q = 0; q < 4; ++q) {
+        const uint32_t off = sw128_offset(r, half * 4 + q);
+        *reinterpret_cast<uint4*>(ptb + off) = make_uint4(pp[q * 4], pp[q * 4 + 1], pp[q * 4 + 2], pp[q * 4 + 3]);
+        *reinterpret_cast<uint4*>(dsb + off) = make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_ready);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[b]);
     }
-    // ---- epilogue: accumulators -> bf16 -> HBM (row = TMEM lane = owned block row) ----
-    mbar_wait(acc_done, (n_it - 1) & 1);
+    mbar_wait(done, 0);
     tc_fence_after();
-    const uint32_t oi = own * 128 + r;
-    const bool valid = oi < (uint32_t)seq_len;
-    const int64_t t = (int64_t)seq_start + oi;
-    constexpr int NOUT = (MODE == MODE_DKDV) ? 2 : 1;
-#pragma unroll
-    for (int which = 0; which < NOUT; ++which) {
-      // DKDV: acc0 = dV -> out1 (v grads), acc1 = dK -> out0 (k grads).  DQ: acc0 = dQ -> out0.
-      const uint32_t tm = (which == 0) ? tmem_A0 : tmem_A1;
-      __nv_bfloat16* dst;
-      if (MODE == MODE_DKDV) dst = (which == 0) ? (out1 + t * ld1 + head * 128) : (out0 + t * ld0 + head * 128);
-      else dst = out0 + t * ld0 + head * 128;
-      const bool rope = rope_pos != nullptr && !(MODE == MODE_DKDV && which == 0);   // dQ and dK, never dV
-      uint32_t a[32], b[32];
-      tmem_ld_32x32b_x32(tm + lane_off + c0, a);
-      tmem_ld_32x32b_x32(tm + lane_off + c0 + 64, b);
-      tmem_ld_wait();
-      if (valid) {
-        const int p = rope ? rope_pos[t] : 0;
-        const __nv_bfloat16* cs = cos_t + (int64_t)p * 128;
-        const __nv_bfloat16* sn = sin_t + (int64_t)p * 128;
-#pragma unroll
-        for (uint32_t i = 0; i < 32; i += 8) {
-          uint4 o1, o2;
-          uint32_t* p1 = &o1.x; uint32_t* p2 = &o2.x;
-          uint4 c1 = make_uint4(0, 0, 0, 0), s1 = c1, c2 = c1, s2 = c1;
-          if (rope) {
-            c1 = *reinterpret_cast<const uint4*>(cs + c0 + i);      s1 = *reinterpret_cast<const uint4*>(sn + c0 + i);
-            c2 = *reinterpret_cast<const uint4*>(cs + 64 + c0 + i); s2 = *reinterpret_cast<const uint4*>(sn + 64 + c0 + i);
-          }
-          const uint32_t* pc1 = &c1.x; const uint32_t* ps1 = &s1.x; const uint32_t* pc2 = &c2.x; const uint32_t* ps2 = &s2.x;
-#pragma unroll
-          for (uint32_t q = 0; q < 4; ++q) {
-            const uint32_t xa = pack_bf16x2(__uint_as_float(a[i + 2 * q]), __uint_as_float(a[i + 2 * q + 1]));
-            const uint32_t xb = pack_bf16x2(__uint_as_float(b[i + 2 * q]), __uint_as_float(b[i + 2 * q + 1]));
-            if (rope) {   // rotation by -theta on the bf16 gradient, same rounding points as rope_kernel(sign = -1)
-              const float y1l = bf16_round(bf16_lo(xa) * bf16_lo(pc1[q])) + bf16_round(bf16_lo(xb) * bf16_lo(ps1[q]));
-              const float y1h = bf16_round(bf16_hi(xa) * bf16_hi(pc1[q])) + bf16_round(bf16_hi(xb) * bf16_hi(ps1[q]));
-              const float y2l = bf16_round(bf16_lo(xb) * bf16_lo(pc2[q])) + bf16_round(-bf16_lo(xa) * bf16_lo(ps2[q]));
-              const float y2h = bf16_round(bf16_hi(xb) * bf16_hi(pc2[q])) + bf16_round(-bf16_hi(xa) * bf16_hi(ps2[q]));
-              p1[q] = pack_bf16x2(y1l, y1h);
-              p2[q] = pack_bf16x2(y2l, y2h);
-            } else {
-              p1[q] = xa;
-              p2[q] = xb;
-            }
-          }
-          *reinterpret_cast<uint4*>(dst + c0 + i) = o1;
-          *reinterpret_cast<uint4*>(dst + c0 + 64 + i) = o2;
-        }
-      }
-    }
+    const bool valid = kj < (uint32_t)seq_len;
+    const int64_t tok = (int64_t)seq_start + kj;
+    store_acc_rows(tmem_dV, lane_off, half * 32, valid, dv + tok * lddv + head * 128, false, 0, cos_t, sin_t);
+    store_acc_rows(tmem_dK, lane_off, half * 32, valid, dk + tok * lddk + head * 128, rope_pos != nullptr,
+                   (rope_pos != nullptr && valid) ? rope_pos[tok] : 0, cos_t, sin_t);
   }
 
   tc_fence_before();
@@ -342,16 +536,14 @@ extern "C" int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
              "nv_attn_bwd: leading-dimension alignment");
   CUtensorMap tq, tk, tv, tdo;
   int rc;
-  if ((rc = make_tmap_2d(&tq, q, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldq * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d(&tk, k, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldk * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d(&tv, v, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldv * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d(&tdo, dout, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)lddo * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d(&tq, q, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldq * 2, 64, 64))) return rc;
+  if ((rc = make_tmap_2d(&tk, k, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldk * 2, 64, 64))) return rc;
+  if ((rc = make_tmap_2d(&tv, v, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldv * 2, 64, 64))) return rc;
+  if ((rc = make_tmap_2d(&tdo, dout, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)lddo * 2, 64, 64))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    NV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<MODE_DKDV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 AttnBwdSmem::DYN_BYTES));
-    NV_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<MODE_DQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 AttnBwdSmem::DYN_BYTES));
+    NV_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::DYN_BYTES));
+    NV_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::DYN_BYTES));
     attr_set = true;
   }
   {
@@ -360,15 +552,15 @@ extern "C" int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
         reinterpret_cast<const __nv_bfloat16*>(o), ldo, reinterpret_cast<const __nv_bfloat16*>(dout), lddo, dvec, T, H);
     NV_LAUNCH_CHECK();
   }
+  const __nv_bfloat16* c = reinterpret_cast<const __nv_bfloat16*>(cos_t);
+  const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(sin_t);
   dim3 grid(total_blocks, H);
-  attn_bwd_kernel<MODE_DKDV><<<grid, AB_THREADS, AttnBwdSmem::DYN_BYTES, stream>>>(
+  attn_bwd_dkv_kernel<<<grid, AB_THREADS, DkvSmem::DYN_BYTES, stream>>>(
       tq, tk, tv, tdo, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dk), lddk, reinterpret_cast<__nv_bfloat16*>(dv), lddv,
-      cu_seqlens, B, T, scale, rope_pos, reinterpret_cast<const __nv_bfloat16*>(cos_t),
-      reinterpret_cast<const __nv_bfloat16*>(sin_t));
+      cu_seqlens, B, T, scale, rope_pos, c, s);
   NV_LAUNCH_CHECK();
-  attn_bwd_kernel<MODE_DQ><<<grid, AB_THREADS, AttnBwdSmem::DYN_BYTES, stream>>>(
-      tq, tk, tv, tdo, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dq), lddq, nullptr, 0, cu_seqlens, B, T, scale, rope_pos,
-      reinterpret_cast<const __nv_bfloat16*>(cos_t), reinterpret_cast<const __nv_bfloat16*>(sin_t));
+  attn_bwd_dq_kernel<<<grid, AB_THREADS, DqSmem::DYN_BYTES, stream>>>(
+      tq, tk, tv, tdo, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dq), lddq, cu_seqlens, B, T, scale, rope_pos, c, s);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }
