@@ -307,13 +307,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 // dk/dv pass (transposed scores: TMEM lanes = keys)
 // ======================================================================================================
 struct DkvSmem {
-  static constexpr uint32_t NST = 2;
+  static constexpr uint32_t NST = 3;
   static constexpr uint32_t K_OFF = 0, V_OFF = AB_T128;
   static constexpr uint32_t QO_OFF = 2 * AB_T128;                 // NST x (Q 16K | dO 16K)
-  static constexpr uint32_t PT_OFF = QO_OFF + NST * 2 * AB_T64;   // 2 x 16K
-  static constexpr uint32_t DST_OFF = PT_OFF + 2 * AB_PS;         // 2 x 16K
-  static constexpr uint32_t BAR_OFF = DST_OFF + 2 * AB_PS;
-  // res_full, qo_full[2], qo_empty[2], sdp_full[2], sdp_empty[2], pds_full[2], pds_empty[2], done
+  static constexpr uint32_t PT_OFF = QO_OFF + NST * 2 * AB_T64;   // 16K (single buffer: the accumulate MMAs of sub-block n
+  static constexpr uint32_t DST_OFF = PT_OFF + AB_PS;             // 16K  finish long before sub-block n+1 is ready to store)
+  static constexpr uint32_t BAR_OFF = DST_OFF + AB_PS;
+  // res_full, qo_full[3], qo_empty[3], sdp_full[2], sdp_empty[2], pds_full, pds_empty, done
   static constexpr uint32_t NUM_BARS = 14;
   static constexpr uint32_t DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
@@ -335,12 +335,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* sDST = smem + L::DST_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* res_full = bars + 0;
-  uint64_t* qo_full = bars + 1;     // [2]
-  uint64_t* qo_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;    // [2]
-  uint64_t* sdp_empty = bars + 7;   // [2]
-  uint64_t* pds_full = bars + 9;    // [2]
-  uint64_t* pds_empty = bars + 11;  // [2]
+  uint64_t* qo_full = bars + 1;     // [3]
+  uint64_t* qo_empty = bars + 4;    // [3]
+  uint64_t* sdp_full = bars + 7;    // [2]
+  uint64_t* sdp_empty = bars + 9;   // [2]
+  uint64_t* pds_full = bars + 11;
+  uint64_t* pds_empty = bars + 12;
   uint64_t* done = bars + 13;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
   __shared__ float s_stats[8][2][32];   // per compute warp: LSE*log2e and D of its 32 query columns
@@ -357,11 +357,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
     mbar_init(res_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&qo_full[i], 1);  mbar_init(&qo_empty[i], 1);
-      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
-      mbar_init(&pds_full[i], 8); mbar_init(&pds_empty[i], 1);
-    }
+    for (int i = 0; i < 3; ++i) { mbar_init(&qo_full[i], 1); mbar_init(&qo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8); }
+    mbar_init(pds_full, 8);
+    mbar_init(pds_empty, 1);
     mbar_init(done, 1);
     fence_mbar_init();
   }
@@ -379,7 +378,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       load_tile<128>(sK, &tmap_k, res_full, col, seq_start + own * 128);
       load_tile<128>(sV, &tmap_v, res_full, col, seq_start + own * 128);
       for (uint32_t n = 0; n < n_it; ++n) {
-        const uint32_t st = n & 1, use = n >> 1;
+        const uint32_t st = n % 3, use = n / 3;
         mbar_wait(&qo_empty[st], (use & 1) ^ 1);
         mbar_arrive_expect_tx(&qo_full[st], 2 * AB_T64);
         load_tile<64>(sQO + st * 2 * AB_T64, &tmap_q, &qo_full[st], col, seq_start + (first + n) * 64);
@@ -390,20 +389,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     if (lane == 0) {
       constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);     // [128 keys] x [64 q], both K-major over hd
       constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);  // P^T/dS^T (K-major over q) x dO_n/Q_n (MN-major)
-      uint64_t k_k[2], v_k[2], pt_k[2], dst_k[2];
+      uint64_t k_k[2], v_k[2];
 #pragma unroll
       for (uint32_t ka = 0; ka < 2; ++ka) {
         k_k[ka] = umma_smem_desc_sw128(smem_u32(sK + ka * AB_A128), 0, 1024);
         v_k[ka] = umma_smem_desc_sw128(smem_u32(sV + ka * AB_A128), 0, 1024);
       }
-#pragma unroll
-      for (uint32_t b = 0; b < 2; ++b) {
-        pt_k[b] = umma_smem_desc_sw128(smem_u32(sPT + b * AB_PS), 0, 1024);
-        dst_k[b] = umma_smem_desc_sw128(smem_u32(sDST + b * AB_PS), 0, 1024);
-      }
+      const uint64_t pt_k = umma_smem_desc_sw128(smem_u32(sPT), 0, 1024);
+      const uint64_t dst_k = umma_smem_desc_sw128(smem_u32(sDST), 0, 1024);
       auto issue_sdp = [&](uint32_t n) {
-        const uint32_t st = n & 1, b = n & 1;
-        mbar_wait(&qo_full[st], (n >> 1) & 1);
+        const uint32_t st = n % 3, b = n & 1;
+        mbar_wait(&qo_full[st], (n / 3) & 1);
         mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
         tc_fence_after();
         const uint32_t qbase = smem_u32(sQO + st * 2 * AB_T64), obase = qbase + AB_T64;
@@ -426,19 +422,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(res_full, 0);
       issue_sdp(0);
       for (uint32_t n = 0; n < n_it; ++n) {
-        // NB: with 2 stream stages, Q_{n+1}/dO_{n+1} land in the stage that sub-block n-1 released
         if (n + 1 < n_it) issue_sdp(n + 1);
-        const uint32_t st = n & 1, b = n & 1;
-        mbar_wait(&pds_full[b], (n >> 1) & 1);
+        const uint32_t st = n % 3;
+        mbar_wait(pds_full, n & 1);
         tc_fence_after();
         // contraction over the 64 queries (4 k-steps); B rows = queries, 64-wide hd atoms AB_A64 apart
         const uint64_t om = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64 + AB_T64), AB_A64, 1024);
         const uint64_t qm = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64), AB_A64, 1024);
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dV, pt_k[b] + ks * 2, om + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
+        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dV, pt_k + ks * 2, om + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dK, dst_k[b] + ks * 2, qm + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
-        umma_commit(&pds_empty[b]);
+        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dK, dst_k + ks * 2, qm + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
+        umma_commit(pds_empty);
         umma_commit(&qo_empty[st]);
       }
       umma_commit(done);
@@ -489,9 +484,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         pp[i >> 1] = pack_bf16x2(p0, p1);
         dd[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[i]) - d2.x) * scale, p1 * (__uint_as_float(dv[i + 1]) - d2.y) * scale);
       }
-      mbar_wait(&pds_empty[b], ((n >> 1) & 1) ^ 1);
-      uint8_t* ptb = sPT + b * AB_PS;
-      uint8_t* dsb = sDST + b * AB_PS;
+      mbar_wait(pds_empty, (n & 1) ^ 1);                   // accumulate MMAs of sub-block n-1 have consumed P^T / dS^T
+      uint8_t* ptb = sPT;
+      uint8_t* dsb = sDST;
 #pragma unroll
       for (uint32_t q = 0; q < 4; ++q) {
         const uint32_t off = sw128_offset(r, half * 4 + q);
@@ -501,7 +496,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       fence_proxy_async_smem();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&pds_full[b]);
+      if (lane == 0) mbar_arrive(pds_full);
     }
     mbar_wait(done, 0);
     tc_fence_after();
