@@ -69,6 +69,10 @@ int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* dvec, void* dq, int64_t lddq,
                 void* dk, int64_t lddk, void* dv, int64_t lddv, const int* cu_seqlens, int B, int T, int H, int head_dim,
                 int total_blocks, float scale, const int* rope_pos, const void* cos_t, const void* sin_t, void* stream);
+/* Developer hook (no reference counterpart): per-CTA SM-clock phase trace of the last nv_attn_bwd (kernel 0 = dk/dv
+ * pass, 1 = dq pass).  Returns the number of 64-bit words copied, 0 unless built with -DNV_ATTN_TRACE
+ * (tools/attn_trace.py). */
+int nv_debug_attn_trace(int kernel, unsigned long long* out, int max_words);
 
 /* ---- row-wise LM kernels (csrc/lm_ops.cu) ---------------------------------------------------------------
  * LlamaRMSNorm, rotate-half RoPE, SwiGLU (HF LLaMA via models/modified_lm.py:112-116); embedding gather +

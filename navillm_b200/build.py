@@ -28,6 +28,8 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo", "--use_fast_math", "-Xcompiler", "-fPIC",
     "--expt-relaxed-constexpr", "-Xptxas", "-v", "-DNDEBUG",
 ]
+# developer-only extra flags (e.g. NV_NVCC_EXTRA="-DNV_ATTN_TRACE" for the in-kernel phase trace of tools/attn_trace.py)
+NVCC_FLAGS += os.environ.get("NV_NVCC_EXTRA", "").split()
 
 
 def _nvcc() -> str:

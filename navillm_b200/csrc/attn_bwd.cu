@@ -33,6 +33,17 @@ constexpr uint32_t AB_A64 = 64 * 128;        // one atom of a 64-row tile
 constexpr uint32_t AB_PS = 128 * 64 * 2;     // [128 rows x 64 cols] bf16 = one 16 KB atom (P / dS operands)
 constexpr float LOG2E = 1.4426950408889634f;
 
+// Developer phase trace (compiled in only with -DNV_ATTN_TRACE, see tools/attn_trace.py): SM-clock stamps of the
+// pipeline events of the CTAs of one head, read back through nv_debug_attn_trace().
+#ifdef NV_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[2][256 * 64];
+#define AB_TR(k, slot) do { if (blockIdx.y == 5 && blockIdx.x < 256) g_attn_trace[k][blockIdx.x * 64 + (slot)] = clock64(); } while (0)
+#define AB_TRV(k, slot, v) do { if (blockIdx.y == 5 && blockIdx.x < 256) g_attn_trace[k][blockIdx.x * 64 + (slot)] = (v); } while (0)
+#else
+#define AB_TR(k, slot) do {} while (0)
+#define AB_TRV(k, slot, v) do {} while (0)
+#endif
+
 __device__ __forceinline__ bool locate_block_bwd(const int* __restrict__ cu, int B, uint32_t blk, int& seq_start,
                                                  int& seq_len, uint32_t& idx) {
   for (int b = 0; b < B; ++b) {
@@ -156,13 +167,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   uint64_t* done = bars + 15;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
   int seq_start = 0, seq_len = 0;
   uint32_t own = 0;
   if (!locate_block_bwd(cu_seqlens, B, gridDim.x - 1 - blockIdx.x, seq_start, seq_len, own)) return;  // heavy first
   // 64-key sub-blocks 0 .. n_sub-1 cover keys [0, min((own+1)*128, len))
   const uint32_t n_sub = min(2 * own + 2, (uint32_t)(seq_len + 63) / 64);
+  if (threadIdx.x == 0) {
+    AB_TR(1, 0); AB_TRV(1, 3, n_sub);
+#ifdef NV_ATTN_TRACE
+    unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); AB_TRV(1, 4, sm);
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); AB_TRV(1, 5, gt);
+#endif
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
@@ -181,71 +199,78 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_dQ = tmem_base + 256;
+  if (threadIdx.x == 0) AB_TR(1, 1);
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int32_t col = head * 128;
+    const int32_t col = head * 128;
+    if (elect_one()) {
       mbar_arrive_expect_tx(res_full, 2 * AB_T128);
       load_tile<128>(sQ, &tmap_q, res_full, col, seq_start + own * 128);
       load_tile<128>(sdO, &tmap_do, res_full, col, seq_start + own * 128);
-      for (uint32_t n = 0; n < n_sub; ++n) {
-        const uint32_t st = n % 3, use = n / 3;
-        mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+    }
+    __syncwarp();
+    for (uint32_t n = 0; n < n_sub; ++n) {
+      const uint32_t st = n % 3, use = n / 3;
+      mbar_wait(&kv_empty[st], (use & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * AB_T64);
         load_tile<64>(sKV + st * 2 * AB_T64, &tmap_k, &kv_full[st], col, seq_start + n * 64);
         load_tile<64>(sKV + st * 2 * AB_T64 + AB_T64, &tmap_v, &kv_full[st], col, seq_start + n * 64);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // [128 q] x [64 keys], both K-major over hd
-      constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);  // dS (K-major over keys) x K_n (MN-major: hd contiguous)
-      uint64_t q_k[2], o_k[2], ds_k[2];
+    // whole warp runs the issue loop (uniform registers, see elect_one()); one elected lane issues
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // [128 q] x [64 keys], both K-major over hd
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);  // dS (K-major over keys) x K_n (MN-major: hd contiguous)
+    const uint64_t q_k = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+    const uint64_t o_k = umma_smem_desc_sw128(smem_u32(sdO), 0, 1024);
+    const uint64_t ds_k = umma_smem_desc_sw128(smem_u32(sDS), 0, 1024);
+    auto issue_sdp = [&](uint32_t n) {
+      const uint32_t st = n % 3, b = n & 1;
+      mbar_wait(&kv_full[st], (n / 3) & 1);
+      mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t kd = umma_smem_desc_sw128(smem_u32(sKV + st * 2 * AB_T64), 0, 1024);
+        const uint64_t vd = kd + (AB_T64 >> 4);
 #pragma unroll
-      for (uint32_t ka = 0; ka < 2; ++ka) {
-        q_k[ka] = umma_smem_desc_sw128(smem_u32(sQ + ka * AB_A128), 0, 1024);
-        o_k[ka] = umma_smem_desc_sw128(smem_u32(sdO + ka * AB_A128), 0, 1024);
-      }
-#pragma unroll
-      for (uint32_t b = 0; b < 2; ++b) ds_k[b] = umma_smem_desc_sw128(smem_u32(sDS + b * AB_PS), 0, 1024);
-      auto issue_sdp = [&](uint32_t n) {
-        const uint32_t st = n % 3, b = n & 1;
-        mbar_wait(&kv_full[st], (n / 3) & 1);
-        mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t kbase = smem_u32(sKV + st * 2 * AB_T64), vbase = kbase + AB_T64;
-#pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t kd = umma_smem_desc_sw128(kbase + ka * AB_A64, 0, 1024);
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_base + b * 64, q_k[ka] + ks * 2, kd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
-        }
+            umma_f16_ss(tmem_base + b * 64, q_k + ka * (AB_A128 >> 4) + ks * 2, kd + ka * (AB_A64 >> 4) + ks * 2, idesc_s,
+                        (ka | ks) ? 1u : 0u);
 #pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t vd = umma_smem_desc_sw128(vbase + ka * AB_A64, 0, 1024);
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_base + 128 + b * 64, o_k[ka] + ks * 2, vd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
-        }
+            umma_f16_ss(tmem_base + 128 + b * 64, o_k + ka * (AB_A128 >> 4) + ks * 2, vd + ka * (AB_A64 >> 4) + ks * 2,
+                        idesc_s, (ka | ks) ? 1u : 0u);
         umma_commit(&sdp_full[b]);
-      };
-      mbar_wait(res_full, 0);
-      issue_sdp(0);
-      for (uint32_t n = 0; n < n_sub; ++n) {
-        if (n + 1 < n_sub) issue_sdp(n + 1);
-        const uint32_t st = n % 3, b = n & 1;
-        mbar_wait(&ds_full[b], (n >> 1) & 1);
-        tc_fence_after();
+        if (n < 8) AB_TR(1, 10 + 2 * n);
+      }
+      __syncwarp();
+    };
+    mbar_wait(res_full, 0);
+    if (lane == 0) AB_TR(1, 2);
+    issue_sdp(0);
+    for (uint32_t n = 0; n < n_sub; ++n) {
+      if (n + 1 < n_sub) issue_sdp(n + 1);
+      const uint32_t st = n % 3, b = n & 1;
+      mbar_wait(&ds_full[b], (n >> 1) & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        if (n < 8) AB_TR(1, 11 + 2 * n);
         // dQ += dS K_n : contraction over the 64 keys (4 k-steps); B rows = keys, 64-wide hd atoms AB_A64 apart
         const uint64_t km = umma_smem_desc_sw128(smem_u32(sKV + st * 2 * AB_T64), AB_A64, 1024);
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks)
-          umma_f16_ss(tmem_dQ, ds_k[b] + ks * 2, km + ks * 128, idesc_dq, (n | ks) ? 1u : 0u);
+          umma_f16_ss(tmem_dQ, ds_k + b * (AB_PS >> 4) + ks * 2, km + ks * 128, idesc_dq, (n | ks) ? 1u : 0u);
         umma_commit(&ds_empty[b]);
         umma_commit(&kv_empty[st]);
+        if (n + 1 == n_sub) umma_commit(done);
       }
-      umma_commit(done);
+      __syncwarp();
     }
   } else {
     const uint32_t quarter = warp & 3, half = (warp - 2) >> 2;
@@ -261,6 +286,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     for (uint32_t n = 0; n < n_sub; ++n) {
       const uint32_t b = n & 1;
       mbar_wait(&sdp_full[b], (n >> 1) & 1);
+      if (warp == 2 && lane == 0 && n < 8) AB_TR(1, 30 + 2 * n);
       tc_fence_after();
       uint32_t sv[32], dv[32];
       tmem_ld_32x32b_x32(tmem_base + b * 64 + lane_off + half * 32, sv);
@@ -291,16 +317,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[b]);
+      if (warp == 2 && lane == 0 && n < 8) AB_TR(1, 31 + 2 * n);
     }
     mbar_wait(done, 0);
+    if (warp == 2 && lane == 0) AB_TR(1, 50);
     tc_fence_after();
     store_acc_rows(tmem_dQ, lane_off, half * 32, row_valid, dq + tok * lddq + head * 128, rope_pos != nullptr,
                    (rope_pos != nullptr && row_valid) ? rope_pos[tok] : 0, cos_t, sin_t);
+    if (warp == 2 && lane == 0) AB_TR(1, 51);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (threadIdx.x == 32) AB_TR(1, 52);
 }
 
 // ======================================================================================================
@@ -345,7 +375,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
   __shared__ float s_stats[8][2][32];   // per compute warp: LSE*log2e and D of its 32 query columns
 
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
   int seq_start = 0, seq_len = 0;
   uint32_t own = 0;
@@ -372,71 +402,75 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   const uint32_t tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 384;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const int32_t col = head * 128;
+    const int32_t col = head * 128;
+    if (elect_one()) {
       mbar_arrive_expect_tx(res_full, 2 * AB_T128);
       load_tile<128>(sK, &tmap_k, res_full, col, seq_start + own * 128);
       load_tile<128>(sV, &tmap_v, res_full, col, seq_start + own * 128);
-      for (uint32_t n = 0; n < n_it; ++n) {
-        const uint32_t st = n % 3, use = n / 3;
-        mbar_wait(&qo_empty[st], (use & 1) ^ 1);
+    }
+    __syncwarp();
+    for (uint32_t n = 0; n < n_it; ++n) {
+      const uint32_t st = n % 3, use = n / 3;
+      mbar_wait(&qo_empty[st], (use & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&qo_full[st], 2 * AB_T64);
         load_tile<64>(sQO + st * 2 * AB_T64, &tmap_q, &qo_full[st], col, seq_start + (first + n) * 64);
         load_tile<64>(sQO + st * 2 * AB_T64 + AB_T64, &tmap_do, &qo_full[st], col, seq_start + (first + n) * 64);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);     // [128 keys] x [64 q], both K-major over hd
-      constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);  // P^T/dS^T (K-major over q) x dO_n/Q_n (MN-major)
-      uint64_t k_k[2], v_k[2];
+    // whole warp runs the issue loop (uniform registers, see elect_one()); one elected lane issues
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);     // [128 keys] x [64 q], both K-major over hd
+    constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);  // P^T/dS^T (K-major over q) x dO_n/Q_n (MN-major)
+    const uint64_t k_k = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
+    const uint64_t v_k = umma_smem_desc_sw128(smem_u32(sV), 0, 1024);
+    const uint64_t pt_k = umma_smem_desc_sw128(smem_u32(sPT), 0, 1024);
+    const uint64_t dst_k = umma_smem_desc_sw128(smem_u32(sDST), 0, 1024);
+    auto issue_sdp = [&](uint32_t n) {
+      const uint32_t st = n % 3, b = n & 1;
+      mbar_wait(&qo_full[st], (n / 3) & 1);
+      mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t qd = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64), 0, 1024);
+        const uint64_t od = qd + (AB_T64 >> 4);
 #pragma unroll
-      for (uint32_t ka = 0; ka < 2; ++ka) {
-        k_k[ka] = umma_smem_desc_sw128(smem_u32(sK + ka * AB_A128), 0, 1024);
-        v_k[ka] = umma_smem_desc_sw128(smem_u32(sV + ka * AB_A128), 0, 1024);
-      }
-      const uint64_t pt_k = umma_smem_desc_sw128(smem_u32(sPT), 0, 1024);
-      const uint64_t dst_k = umma_smem_desc_sw128(smem_u32(sDST), 0, 1024);
-      auto issue_sdp = [&](uint32_t n) {
-        const uint32_t st = n % 3, b = n & 1;
-        mbar_wait(&qo_full[st], (n / 3) & 1);
-        mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t qbase = smem_u32(sQO + st * 2 * AB_T64), obase = qbase + AB_T64;
-#pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t qd = umma_smem_desc_sw128(qbase + ka * AB_A64, 0, 1024);
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_base + b * 64, k_k[ka] + ks * 2, qd + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
-        }
+            umma_f16_ss(tmem_base + b * 64, k_k + ka * (AB_A128 >> 4) + ks * 2, qd + ka * (AB_A64 >> 4) + ks * 2, idesc_s,
+                        (ka | ks) ? 1u : 0u);
 #pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
-          const uint64_t od = umma_smem_desc_sw128(obase + ka * AB_A64, 0, 1024);
+        for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_base + 128 + b * 64, v_k[ka] + ks * 2, od + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
-        }
+            umma_f16_ss(tmem_base + 128 + b * 64, v_k + ka * (AB_A128 >> 4) + ks * 2, od + ka * (AB_A64 >> 4) + ks * 2,
+                        idesc_s, (ka | ks) ? 1u : 0u);
         umma_commit(&sdp_full[b]);
-      };
-      mbar_wait(res_full, 0);
-      issue_sdp(0);
-      for (uint32_t n = 0; n < n_it; ++n) {
-        if (n + 1 < n_it) issue_sdp(n + 1);
-        const uint32_t st = n % 3;
-        mbar_wait(pds_full, n & 1);
-        tc_fence_after();
+      }
+      __syncwarp();
+    };
+    mbar_wait(res_full, 0);
+    issue_sdp(0);
+    for (uint32_t n = 0; n < n_it; ++n) {
+      if (n + 1 < n_it) issue_sdp(n + 1);
+      const uint32_t st = n % 3;
+      mbar_wait(pds_full, n & 1);
+      tc_fence_after();
+      if (elect_one()) {
         // contraction over the 64 queries (4 k-steps); B rows = queries, 64-wide hd atoms AB_A64 apart
-        const uint64_t om = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64 + AB_T64), AB_A64, 1024);
         const uint64_t qm = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64), AB_A64, 1024);
+        const uint64_t om = qm + (AB_T64 >> 4);
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dV, pt_k + ks * 2, om + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dK, dst_k + ks * 2, qm + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
         umma_commit(pds_empty);
         umma_commit(&qo_empty[st]);
+        if (n + 1 == n_it) umma_commit(done);
       }
-      umma_commit(done);
+      __syncwarp();
     }
   } else {
     const uint32_t cw = warp - 2;
@@ -513,6 +547,20 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 }
 
 }  // namespace nv
+
+// Developer hook: copy the phase trace of the last nv_attn_bwd (kernel 0 = dk/dv pass, 1 = dq pass) to the host.
+// Returns the number of 64-bit words written, 0 when the library was built without -DNV_ATTN_TRACE.
+extern "C" int nv_debug_attn_trace(int kernel, unsigned long long* out, int max_words) {
+#ifdef NV_ATTN_TRACE
+  if (kernel < 0 || kernel > 1 || !out) return 0;
+  const int n = max_words < 256 * 64 ? max_words : 256 * 64;
+  if (cudaMemcpyFromSymbol(out, nv::g_attn_trace, (size_t)n * 8, (size_t)kernel * 256 * 64 * 8) != cudaSuccess) return 0;
+  return n;
+#else
+  (void)kernel; (void)out; (void)max_words;
+  return 0;
+#endif
+}
 
 // Inputs: q,k,v (post-RoPE) and o, do as bf16 [T, H*128]-column views; lse [H,T] from the forward.
 // dvec: fp32 workspace [H, T].  Outputs dq, dk, dv: bf16 views with their own leading dimensions.

@@ -72,7 +72,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   uint64_t* pv_done = bars + 11;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
 
   int seq_start = 0, seq_len = 0;
@@ -104,93 +104,98 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
-      const int32_t qcol = head * 128;
-      const int32_t qrow0 = seq_start + q0;
+    // (whole warp runs the loop, one elected lane issues: see elect_one() in nv_common.cuh)
+    const int32_t qcol = head * 128;
+    const int32_t qrow0 = seq_start + q0;
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * ATT_TILE_BYTES);
 #pragma unroll
       for (int t = 0; t < 2; ++t) {
         tma_load_2d(sQ + t * ATT_TILE_BYTES, &tmap_q, q_full, qcol, qrow0 + t * 128);
         tma_load_2d(sQ + t * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmap_q, q_full, qcol + 64, qrow0 + t * 128);
       }
-      for (uint32_t j = 0; j < n_blocks; ++j) {
-        const int32_t krow0 = seq_start + j * 128;
-        mbar_wait(k_empty, (j & 1) ^ 1);
+    }
+    __syncwarp();
+    for (uint32_t j = 0; j < n_blocks; ++j) {
+      const int32_t krow0 = seq_start + j * 128;
+      mbar_wait(k_empty, (j & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(k_full, ATT_TILE_BYTES);
         tma_load_2d(sK, &tmap_k, k_full, qcol, krow0);
         tma_load_2d(sK + ATT_ATOM_BYTES, &tmap_k, k_full, qcol + 64, krow0);
-        const uint32_t st = j & 1;
-        mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+      }
+      __syncwarp();
+      const uint32_t st = j & 1;
+      mbar_wait(&v_empty[st], ((j >> 1) & 1) ^ 1);
+      if (elect_one()) {
         mbar_arrive_expect_tx(&v_full[st], ATT_TILE_BYTES);
         tma_load_2d(sV + st * ATT_TILE_BYTES, &tmap_v, &v_full[st], qcol, krow0);
         tma_load_2d(sV + st * ATT_TILE_BYTES + ATT_ATOM_BYTES, &tmap_v, &v_full[st], qcol + 64, krow0);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // P (K-major) x V (MN-major: hd contiguous)
-      // All operand descriptors are loop-invariant: build them once so that the single issuing thread spends
-      // its cycles on tcgen05.mma, not on descriptor arithmetic (it is the serial bottleneck otherwise).
-      uint64_t qd[2][2], pd[2][2], kd[2], vd[2];
-#pragma unroll
-      for (uint32_t t = 0; t < 2; ++t)
-#pragma unroll
-        for (uint32_t ka = 0; ka < 2; ++ka) {
-          qd[t][ka] = umma_smem_desc_sw128(smem_u32(sQ + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024);
-          pd[t][ka] = umma_smem_desc_sw128(smem_u32(sP + t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES), 0, 1024);
-        }
-#pragma unroll
-      for (uint32_t ka = 0; ka < 2; ++ka) kd[ka] = umma_smem_desc_sw128(smem_u32(sK + ka * ATT_ATOM_BYTES), 0, 1024);
-      // V tile: rows = keys (K dim), 128 B of hd per row per atom; atoms (hd halves) ATT_ATOM_BYTES apart
-#pragma unroll
-      for (uint32_t st = 0; st < 2; ++st) vd[st] = umma_smem_desc_sw128(smem_u32(sV + st * ATT_TILE_BYTES), ATT_ATOM_BYTES, 1024);
-      auto issue_s = [&](uint32_t t) {
+    // The whole warp walks the (uniform) schedule; each group of tcgen05.mma + commit is issued by the elected lane,
+    // with every operand in uniform registers so that the 32/64-cycle MMAs go out back to back.
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, 0, 0);   // Q (K-major) x K (K-major)
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(128, 128, 0, 1);  // P (K-major) x V (MN-major: hd contiguous)
+    const uint64_t qd0 = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
+    const uint64_t pd0 = umma_smem_desc_sw128(smem_u32(sP), 0, 1024);
+    const uint64_t kd0 = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
+    // V tile: rows = keys (K dim), 128 B of hd per row per atom; atoms (hd halves) ATT_ATOM_BYTES apart
+    const uint64_t vd0 = umma_smem_desc_sw128(smem_u32(sV), ATT_ATOM_BYTES, 1024);
+    auto issue_s = [&](uint32_t t, uint64_t* extra_commit) {
+      if (elect_one()) {
         const uint32_t d_tmem = tmem_base + t * 128;
 #pragma unroll
         for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(d_tmem, qd[t][ka] + ks * 2, kd[ka] + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
+            umma_f16_ss(d_tmem, qd0 + ((t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES) >> 4) + ks * 2,
+                        kd0 + ((ka * ATT_ATOM_BYTES) >> 4) + ks * 2, idesc_s, (ka | ks) ? 1u : 0u);
         umma_commit(&s_full[t]);
-      };
-      auto issue_pv = [&](uint32_t t, uint32_t st, bool accumulate) {
+        if (extra_commit) umma_commit(extra_commit);
+      }
+      __syncwarp();
+    };
+    auto issue_pv = [&](uint32_t t, uint32_t st, bool accumulate, uint64_t* extra_commit) {
+      if (elect_one()) {
         const uint32_t d_tmem = tmem_base + 256 + t * 128;
 #pragma unroll
         for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)   // key rows ka*64 + ks*16 -> byte offset * 128 >> 4
-            umma_f16_ss(d_tmem, pd[t][ka] + ks * 2, vd[st] + ((ka * 64 + ks * 16) * 128 >> 4), idesc_pv,
+            umma_f16_ss(d_tmem, pd0 + ((t * ATT_TILE_BYTES + ka * ATT_ATOM_BYTES) >> 4) + ks * 2,
+                        vd0 + ((st * ATT_TILE_BYTES) >> 4) + ((ka * 64 + ks * 16) * 128 >> 4), idesc_pv,
                         (accumulate || (ka | ks)) ? 1u : 0u);
         umma_commit(&pv_done[t]);
-      };
-      mbar_wait(q_full, 0);
-      mbar_wait(k_full, 0);
-      tc_fence_after();
-      for (uint32_t t = 0; t < 2; ++t)
-        if (tile_on(t, 0)) issue_s(t);
-      umma_commit(k_empty);
-      for (uint32_t j = 0; j < n_blocks; ++j) {
-        const uint32_t st = j & 1;
-        const bool have_next = (j + 1 < n_blocks);
-        bool k_next_waited = false, v_waited = false;
-        for (uint32_t t = 0; t < 2; ++t) {
-          if (!tile_on(t, j)) continue;
-          mbar_wait(&p_ready[t], j & 1);           // tile t processes every block 0..its last, so its phase index is j
-          tc_fence_after();
-          if (have_next && tile_on(t, j + 1)) {
-            if (!k_next_waited) { mbar_wait(k_full, (j + 1) & 1); tc_fence_after(); k_next_waited = true; }
-            issue_s(t);                             // S_t(j+1) overlaps the other tile's softmax
-            if (t == last_tile(j + 1)) umma_commit(k_empty);
-          }
-          if (!v_waited) { mbar_wait(&v_full[st], (j >> 1) & 1); tc_fence_after(); v_waited = true; }
-          issue_pv(t, st, j > 0);
-          if (t == last_tile(j)) umma_commit(&v_empty[st]);
-        }
-        // a block seen only by tile 1 whose S could not be issued from tile 0's branch: handled above because
-        // tile_on(1, j+1) implies tile_on(1, j); tile 0 dropping out at the last block needs no S.
+        if (extra_commit) umma_commit(extra_commit);
       }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(k_full, 0);
+    tc_fence_after();
+    for (uint32_t t = 0; t < 2; ++t)
+      if (tile_on(t, 0)) issue_s(t, t == last_tile(0) ? k_empty : nullptr);
+    for (uint32_t j = 0; j < n_blocks; ++j) {
+      const uint32_t st = j & 1;
+      const bool have_next = (j + 1 < n_blocks);
+      bool k_next_waited = false, v_waited = false;
+      for (uint32_t t = 0; t < 2; ++t) {
+        if (!tile_on(t, j)) continue;
+        mbar_wait(&p_ready[t], j & 1);           // tile t processes every block 0..its last, so its phase index is j
+        tc_fence_after();
+        if (have_next && tile_on(t, j + 1)) {
+          if (!k_next_waited) { mbar_wait(k_full, (j + 1) & 1); tc_fence_after(); k_next_waited = true; }
+          issue_s(t, t == last_tile(j + 1) ? k_empty : nullptr);   // S_t(j+1) overlaps the other tile's softmax
+        }
+        if (!v_waited) { mbar_wait(&v_full[st], (j >> 1) & 1); tc_fence_after(); v_waited = true; }
+        issue_pv(t, st, j > 0, t == last_tile(j) ? &v_empty[st] : nullptr);
+      }
+      // a block seen only by tile 1 whose S could not be issued from tile 0's branch: handled above because
+      // tile_on(1, j+1) implies tile_on(1, j); tile 0 dropping out at the last block needs no S.
     }
   } else {
     // ================================ softmax groups ================================

@@ -76,7 +76,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   uint64_t* tmem_empty = bars + 2 * STAGES + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
-  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t warp = warp_id_uniform();
   const uint32_t lane = threadIdx.x & 31;
 
   constexpr uint32_t TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64) ? 64 : (2 * BLOCK_N <= 128) ? 128
@@ -112,14 +112,15 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        uint32_t m_blk, n_blk;
-        tile_coords(tile, num_m, num_n, m_blk, n_blk);
-        const int32_t m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // (the whole warp runs the loop and one elected lane issues: operands stay in uniform registers, see elect_one())
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t m_blk, n_blk;
+      tile_coords(tile, num_m, num_n, m_blk, n_blk);
+      const int32_t m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
+      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
           const int32_t k0 = kb * GEMM_BLOCK_K;
           uint8_t* sa = smem_a + stage * L::A_BYTES;
@@ -138,37 +139,39 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             for (uint32_t i = 0; i < BLOCK_N / 64; ++i)
               tma_load_2d(sb + i * (GEMM_BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
           }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
-      // K-major: SBO = 8 rows * 128 B; advance 32 B per UMMA_K inside the 128-byte swizzle span.
-      // MN-major: LBO = one 64-wide MN atom (BLOCK_K rows * 128 B), SBO = 8 K rows; advance 16 K rows.
-      constexpr uint32_t A_LBO = A_MN ? GEMM_BLOCK_K * 128 : 0, B_LBO = B_MN ? GEMM_BLOCK_K * 128 : 0;
-      constexpr uint32_t A_KADV = A_MN ? (GEMM_UMMA_K * 128) >> 4 : (GEMM_UMMA_K * 2) >> 4;
-      constexpr uint32_t B_KADV = B_MN ? (GEMM_UMMA_K * 128) >> 4 : (GEMM_UMMA_K * 2) >> 4;
-      uint32_t stage = 0, phase = 0, iter = 0;
-      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
-        const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    constexpr uint32_t idesc = umma_idesc_bf16(GEMM_BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    // K-major: SBO = 8 rows * 128 B; advance 32 B per UMMA_K inside the 128-byte swizzle span.
+    // MN-major: LBO = one 64-wide MN atom (BLOCK_K rows * 128 B), SBO = 8 K rows; advance 16 K rows.
+    constexpr uint32_t A_LBO = A_MN ? GEMM_BLOCK_K * 128 : 0, B_LBO = B_MN ? GEMM_BLOCK_K * 128 : 0;
+    constexpr uint32_t A_KADV = A_MN ? (GEMM_UMMA_K * 128) >> 4 : (GEMM_UMMA_K * 2) >> 4;
+    constexpr uint32_t B_KADV = B_MN ? (GEMM_UMMA_K * 128) >> 4 : (GEMM_UMMA_K * 2) >> 4;
+    uint32_t stage = 0, phase = 0, iter = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++iter) {
+      const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * L::A_BYTES), A_LBO, 1024);
           const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * L::B_BYTES), B_LBO, 1024);
 #pragma unroll
           for (uint32_t k = 0; k < GEMM_BLOCK_K / GEMM_UMMA_K; ++k)
             umma_f16_ss(tmem_d, adesc + k * A_KADV, bdesc + k * B_KADV, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (kb + 1 == num_kb) umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {

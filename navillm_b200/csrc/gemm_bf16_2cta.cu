@@ -132,7 +132,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2; // used in the leader [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + G2_NUM_BARS);
 
-  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
 
@@ -169,16 +169,17 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        uint32_t m_blk, n_blk;
-        tile_coords2(tile, num_m, num_n, m_blk, n_blk);
-        const int32_t m0 = m_blk * 2 * G2_BM + rank * G2_BM;    // this CTA's A rows
-        // this CTA's half of the B tile (SWIGLU: CTA 0 stages gate rows n.., CTA 1 the matching up rows F + n..)
-        const int32_t n0 = (EPI == EPI_SWIGLU) ? (int32_t)(n_blk * 128 + rank * ea.F) : (int32_t)(n_blk * G2_BN + rank * G2_BNH);
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+    // (the whole warp runs the loop and one elected lane issues: operands stay in uniform registers, see elect_one())
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      uint32_t m_blk, n_blk;
+      tile_coords2(tile, num_m, num_n, m_blk, n_blk);
+      const int32_t m0 = m_blk * 2 * G2_BM + rank * G2_BM;    // this CTA's A rows
+      // this CTA's half of the B tile (SWIGLU: CTA 0 stages gate rows n.., CTA 1 the matching up rows F + n..)
+      const int32_t n0 = (EPI == EPI_SWIGLU) ? (int32_t)(n_blk * 128 + rank * ea.F) : (int32_t)(n_blk * G2_BN + rank * G2_BNH);
+      for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (elect_one()) {
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
           else mbar_arrive_remote(&full_bar[stage], 0);
           const int32_t k0 = kb * G2_BK;
@@ -198,13 +199,14 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             for (uint32_t i = 0; i < G2_BNH / 64; ++i)
               tma_load_2d_2sm(sb + i * (G2_BK * 128), &tmap_b, &full_bar[stage], n0 + i * 64, k0);
           }
-          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader only) =====================
-    if (leader && lane == 0) {
+    if (leader) {
       constexpr uint32_t idesc = umma_idesc_bf16(2 * G2_BM, G2_BN, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 0, B_LBO = B_MN ? G2_BK * 128 : 0;
       constexpr uint32_t A_KADV = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
@@ -218,15 +220,18 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
-          const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * G2_A_BYTES), A_LBO, 1024);
-          const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * G2_B_BYTES), B_LBO, 1024);
+          if (elect_one()) {
+            const uint64_t adesc = umma_smem_desc_sw128(smem_u32(smem_a + stage * G2_A_BYTES), A_LBO, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(smem_u32(smem_b + stage * G2_B_BYTES), B_LBO, 1024);
 #pragma unroll
-          for (uint32_t k = 0; k < G2_BK / 16; ++k)
-            umma_f16_ss_2sm(tmem_d, adesc + k * A_KADV, bdesc + k * B_KADV, idesc, (kb | k) != 0 ? 1u : 0u);
-          umma_commit_2sm(&empty_bar[stage]);
+            for (uint32_t k = 0; k < G2_BK / 16; ++k)
+              umma_f16_ss_2sm(tmem_d, adesc + k * A_KADV, bdesc + k * B_KADV, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_commit_2sm(&empty_bar[stage]);
+            if (kb + 1 == num_kb) umma_commit_2sm(&tmem_full[acc]);
+          }
+          __syncwarp();
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tmem_full[acc]);
       }
     }
   } else {

@@ -148,6 +148,19 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
+// One lane of a converged warp.  tcgen05.mma / commit sequences are issued as
+//     if (elect_one()) { ...MMAs...; umma_commit(bar); }  __syncwarp();
+// from code that the WHOLE warp executes (warp index taken from warp_id_uniform()): descriptors and TMEM addresses
+// then live in uniform registers and consecutive UTCHMMA issue back to back.  Issuing from an `if (lane == 0)`
+// branch instead makes ptxas wrap every MMA in an ELECT / R2UR / BRA.U.ANY waterfall (~100 cycles per MMA, measured
+// with the in-kernel trace of tools/attn_trace.py), which starves the tensor pipe whenever an MMA is shorter than that.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\tselp.u32 %0, 1, 0, e;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ uint32_t warp_id_uniform() { return __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0); }
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16/f16 inputs, fp32 accumulate. One thread issues.
 __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {

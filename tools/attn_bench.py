@@ -26,7 +26,8 @@ def main():
     dev = torch.device("cuda:0")
     H, HD = 32, 128
     for name, seqlens in (("c2_ragged", np.random.RandomState(1234).randint(256, 1025, size=16).tolist()),
-                          ("dense_1024x16", [1024] * 16), ("dense_2048x4", [2048] * 4)):
+                          ("dense_1024x16", [1024] * 16), ("dense_2048x4", [2048] * 4), ("short_128x128", [128] * 128),
+                          ("short_256x64", [256] * 64)):
         T = sum(seqlens)
         qkv = torch.randn(T, 3 * H * HD, device=dev, dtype=torch.bfloat16)
         do = torch.randn(T, H * HD, device=dev, dtype=torch.bfloat16)
