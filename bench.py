@@ -274,6 +274,8 @@ def main():
     ap.add_argument("--cpu-layers", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", type=int, default=N_LAYERS, help="debug only: fewer layers => number is INVALID")
+    ap.add_argument("--grad-sync", default="overlap", choices=["overlap", "end", "none"],
+                    help="debug only (N>1): 'end' = one all-reduce after the backward, 'none' = no reduction => number is INVALID")
     ap.add_argument("--profile", action="store_true", help="for runs under ncu: no e2e / cpu arms, any warm-up count; the printed number is not a bench value")
     a = ap.parse_args()
 
@@ -297,6 +299,9 @@ def main():
         import navillm_b200.nav_model as nm
         nm.VICUNA_7B["num_hidden_layers"] = a.layers
     model = build_model(dev, seed=0)
+    if a.grad_sync != "overlap":
+        model.lang_model.overlap_grad_reduce = False
+    do_sync = world > 1 and a.grad_sync != "none"
     host, meta = make_workload(1234 + rank)
     pinned = {k: v.pin_memory() for k, v in host.items()}
     tgt_pinned = meta["target_cols"].pin_memory()
@@ -315,7 +320,7 @@ def main():
         model.zero_grad(lazy=True)
         loss = nav_step(model, resident, meta, dev, text=text)
         loss.backward()
-        if world > 1:
+        if do_sync:
             model.allreduce_grads()
         return loss
 
@@ -324,7 +329,7 @@ def main():
         d = upload()
         loss = nav_step(model, d, meta, dev)          # tokenises the prompt strings on the host, like the reference
         loss.backward()
-        if world > 1:
+        if do_sync:
             model.allreduce_grads()
         return float(loss.detach())                   # D2H read of the step's result
 
@@ -383,7 +388,7 @@ def main():
             "config": {"workload": "C2 R2R-shaped training step (panorama+navigation fwd+bwd), B=16/GPU, 36x1408 views, hist=8, "
                                    "24 graph nodes, 15 candidates, seq U{256..1024} (packed: pad tokens not computed), Vicuna-7B random init",
                        "layers": a.layers, "real_tokens_per_step": tokens_real, "l2": "inputs_exceed_l2 (13.5 GB of weights streamed per pass)",
-                       "grad_allreduce": "every step, layer slices overlapped with the backward" if world > 1 else "n/a",
+                       "grad_allreduce": ({"overlap": "every step, layer slices overlapped with the backward", "end": "every step, after the backward (debug)", "none": "DISABLED (debug, invalid)"}[a.grad_sync]) if world > 1 else "n/a",
                        "zero_grad": "lazy (first wgrad of a step overwrites: beta=0)", "optimizer_step": "outside the boundary (train.py:86-89), not timed"},
             "e2e": {"value": e2e, "unit": "nav-steps/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / a.steps},

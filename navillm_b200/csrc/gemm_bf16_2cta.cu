@@ -10,8 +10,17 @@
 //   warp 0 (1 lane, both CTAs)  TMA producer; completes transactions on the LEADER's full barrier
 //   warp 1 (1 lane, leader)     tcgen05.mma.cta_group::2 issuer; commits are multicast to both CTAs
 //   warps 2..5 (both CTAs)      epilogue for the CTA's own 128 rows; arrive on the leader's tmem_empty
+//
+// Tile scheduling is DYNAMIC: the leader's producer warp claims pair tiles from a global atomic counter and
+// publishes each claim to every consumer warp of both CTAs through a 4-slot ring in shared memory (TileRing).
+// With a static "tile = cluster + i * clusters" schedule a CTA pair that becomes resident late - because NCCL's
+// all-reduce CTAs (overlapped with the backward) or another kernel still hold its SMs - runs its whole tile list
+// after everybody else has finished, which doubles the GEMM's duration; with claims the late pair simply finds
+// the counter exhausted.  The counter resets itself (the claim that returns the last value stores 0), so launches
+// on one stream, including CUDA-graph replays, need no memset.  tile_counter == nullptr selects the static order.
 #include "nv_common.cuh"
 #include "nv_host.h"
+#include <cstdlib>
 
 namespace nv {
 
@@ -26,8 +35,9 @@ constexpr uint32_t G2_A_BYTES = G2_BM * G2_BK * 2;
 constexpr uint32_t G2_B_BYTES = G2_BNH * G2_BK * 2;
 constexpr uint32_t G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;
 constexpr uint32_t G2_BAR_OFF = G2_STAGES * G2_STAGE_BYTES;
-constexpr uint32_t G2_NUM_BARS = 2 * G2_STAGES + 4;
-constexpr uint32_t G2_DYN_BYTES = G2_BAR_OFF + G2_NUM_BARS * 8 + 16 + 1024;
+constexpr uint32_t G2_SCHED = 4;      // tile-claim ring slots
+constexpr uint32_t G2_NUM_BARS = 2 * G2_STAGES + 4 + 2 * G2_SCHED;
+constexpr uint32_t G2_DYN_BYTES = G2_BAR_OFF + G2_NUM_BARS * 8 + 16 + G2_SCHED * 4 + 1024;
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address -> CTA 0
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -82,6 +92,72 @@ __device__ __forceinline__ void umma_f16_ss_2sm(uint32_t tmem_d, uint64_t adesc,
       : "memory");
 }
 
+// ---- cluster-scope release/acquire on mbarriers (the tile ring carries DATA between the two CTAs) -------------
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void st_shared_cluster_u32(uint32_t* p, uint32_t cta, uint32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u32 [ra], %2;\n\t}"
+      ::"r"(smem_u32(p)), "r"(cta), "r"(v)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_acquire_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = smem_u32(bar);
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(a), "r"(parity) : "memory");
+  } while (!done);
+}
+
+// Ring of claimed tile indices, replicated in both CTAs of the pair.  One publisher (leader CTA, warp 0) and ten
+// consumer warps (leader: MMA + 4 epilogue; peer: producer + 4 epilogue); `empty` lives in the leader.
+struct TileRing {
+  uint64_t* full;    // [G2_SCHED] per CTA, count 1
+  uint64_t* empty;   // [G2_SCHED] in the leader, count 10
+  uint32_t* tiles;   // [G2_SCHED] per CTA
+  uint32_t idx;
+  // whole warp; returns the tile index (>= num_tiles: no more work)
+  __device__ __forceinline__ uint32_t claim(uint32_t* counter, uint32_t total_claims) {
+    const uint32_t slot = idx % G2_SCHED, ph = (idx / G2_SCHED) & 1;
+    ++idx;
+    mbar_wait(&empty[slot], ph ^ 1);
+    if (elect_one()) {
+      const uint32_t t = atomicAdd(counter, 1u);
+      if (t == total_claims - 1) atomicExch(counter, 0u);   // last claim of this launch: ready for the next one
+      tiles[slot] = t;
+      st_shared_cluster_u32(&tiles[slot], 1, t);
+      mbar_arrive_release_cluster(&full[slot], 0);
+      mbar_arrive_release_cluster(&full[slot], 1);
+    }
+    __syncwarp();
+    return *reinterpret_cast<volatile uint32_t*>(&tiles[slot]);
+  }
+  __device__ __forceinline__ uint32_t take(bool leader, uint32_t lane) {
+    const uint32_t slot = idx % G2_SCHED, ph = (idx / G2_SCHED) & 1;
+    ++idx;
+    mbar_wait_acquire_cluster(&full[slot], ph);
+    const uint32_t t = *reinterpret_cast<volatile uint32_t*>(&tiles[slot]);
+    __syncwarp();
+    if (lane == 0) {
+      if (leader) mbar_arrive(&empty[slot]);
+      else mbar_arrive_remote(&empty[slot], 0);
+    }
+    return t;
+  }
+};
+
 __device__ __forceinline__ void tile_coords2(uint32_t tile, uint32_t num_m, uint32_t num_n, uint32_t& m_blk,
                                              uint32_t& n_blk) {
   const uint32_t group_size = G2_GROUP_M * num_n;
@@ -120,7 +196,7 @@ template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        void* __restrict__ Cout, int64_t ldc, const __nv_bfloat16* __restrict__ addend, int64_t ld_add,
-                       uint32_t M, uint32_t N, uint32_t K, uint32_t flags, EpiAux ea) {
+                       uint32_t M, uint32_t N, uint32_t K, uint32_t flags, EpiAux ea, uint32_t* __restrict__ tile_counter) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -131,6 +207,12 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   uint64_t* tmem_full = bars + 2 * G2_STAGES;      // per CTA [2]
   uint64_t* tmem_empty = bars + 2 * G2_STAGES + 2; // used in the leader [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + G2_NUM_BARS);
+  TileRing ring;
+  ring.full = bars + 2 * G2_STAGES + 4;
+  ring.empty = ring.full + G2_SCHED;
+  ring.tiles = tmem_ptr_smem + 4;
+  ring.idx = 0;
+  const bool dyn = tile_counter != nullptr;
 
   const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -146,6 +228,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     for (uint32_t i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);   // multicast commit
       mbar_init(&tmem_empty[i], 8);  // 4 epilogue warps of each CTA
+    }
+    for (uint32_t i = 0; i < G2_SCHED; ++i) {
+      mbar_init(&ring.full[i], 1);
+      mbar_init(&ring.empty[i], 10);
     }
     fence_mbar_init();
   }
@@ -171,7 +257,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     // ===================== TMA producer (both CTAs) =====================
     // (the whole warp runs the loop and one elected lane issues: operands stay in uniform registers, see elect_one())
     uint32_t stage = 0, phase = 0;
-    for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    for (uint32_t it = 0;; ++it) {
+      const uint32_t tile = !dyn ? cluster_id + it * num_clusters
+                                 : (leader ? ring.claim(tile_counter, num_tiles + num_clusters) : ring.take(false, lane));
+      if (tile >= num_tiles) break;
       uint32_t m_blk, n_blk;
       tile_coords2(tile, num_m, num_n, m_blk, n_blk);
       const int32_t m0 = m_blk * 2 * G2_BM + rank * G2_BM;    // this CTA's A rows
@@ -211,8 +300,10 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       constexpr uint32_t A_LBO = A_MN ? G2_BK * 128 : 0, B_LBO = B_MN ? G2_BK * 128 : 0;
       constexpr uint32_t A_KADV = A_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
       constexpr uint32_t B_KADV = B_MN ? (16 * 128) >> 4 : (16 * 2) >> 4;
-      uint32_t stage = 0, phase = 0, iter = 0;
-      for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t iter = 0;; ++iter) {
+        const uint32_t tile = dyn ? ring.take(true, lane) : cluster_id + iter * num_clusters;
+        if (tile >= num_tiles) break;
         const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -239,8 +330,9 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const uint32_t quarter = warp & 3;
     const bool do_add = (flags & 1u) != 0;
     const bool out_f32 = (flags & 2u) != 0;
-    uint32_t iter = 0;
-    for (uint32_t tile = cluster_id; tile < num_tiles; tile += num_clusters, ++iter) {
+    for (uint32_t iter = 0;; ++iter) {
+      const uint32_t tile = dyn ? ring.take(leader, lane) : cluster_id + iter * num_clusters;
+      if (tile >= num_tiles) break;
       uint32_t m_blk, n_blk;
       tile_coords2(tile, num_m, num_n, m_blk, n_blk);
       const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
@@ -434,6 +526,30 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
+// One self-resetting claim counter per (device, stream hash): kernels on one stream never overlap, so they can share
+// it.  NV_GEMM_STATIC_SCHED=1 selects the static schedule (A/B measurements).
+static int tile_counter_for(cudaStream_t stream, uint32_t** out) {
+  constexpr int SLOTS = 64, MAX_DEV = 16;
+  static uint32_t* pool[MAX_DEV] = {nullptr};
+  static int static_sched = -1;
+  if (static_sched < 0) {
+    const char* e = getenv("NV_GEMM_STATIC_SCHED");
+    static_sched = (e && e[0] == '1') ? 1 : 0;
+  }
+  *out = nullptr;
+  if (static_sched) return NV_OK;
+  int dev = 0;
+  NV_CUDA(cudaGetDevice(&dev));
+  NV_REQUIRE(dev >= 0 && dev < MAX_DEV, "tile_counter_for: device index %d", dev);
+  if (!pool[dev]) {
+    NV_CUDA(cudaMalloc(&pool[dev], SLOTS * 128));      // one counter per 128-byte line
+    NV_CUDA(cudaMemset(pool[dev], 0, SLOTS * 128));
+  }
+  const uint64_t h = (reinterpret_cast<uint64_t>(stream) >> 4) * 0x9E3779B97F4A7C15ull;
+  *out = pool[dev] + (h >> 58) * 32;
+  return NV_OK;
+}
+
 template <bool A_MN, bool B_MN, int EPI = EPI_PLAIN>
 static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* C, int64_t ldc, const void* addend,
                             int64_t ld_add, uint32_t M, uint32_t N, uint32_t K, uint32_t flags, cudaStream_t stream,
@@ -446,8 +562,11 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* 
   }
   const uint32_t tiles = ceil_div_u32(M, 2 * G2_BM) * ceil_div_u32(N, EPI == EPI_SWIGLU ? 128u : G2_BN);
   uint32_t clusters = min(tiles, (uint32_t)sm_count() / 2);
+  uint32_t* counter = nullptr;
+  int rc = tile_counter_for(stream, &counter);
+  if (rc) return rc;
   kern<<<clusters * 2, G2_THREADS, G2_DYN_BYTES, stream>>>(ta, tb, C, ldc, reinterpret_cast<const __nv_bfloat16*>(addend),
-                                                            ld_add, M, N, K, flags, ea);
+                                                            ld_add, M, N, K, flags, ea, counter);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }
