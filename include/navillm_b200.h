@@ -109,6 +109,11 @@ int nv_ce_fwd_bwd(const void* logits, int64_t ld, const int* labels, const int* 
  * scatter glue of NavModel.forward_navigation (models/nav_model.py:146-224), forward and backward. */
 int nv_sgemm(const float* A, int64_t lda, int ta, const float* B, int64_t ldb, int tb, float* C, int64_t ldc,
              const float* bias, int M, int N, int K, int accumulate, void* stream);
+/* Same contract on the tensor cores (tcgen05 kind::tf32, fp32 accumulate; csrc/gemm_tf32.cu): the numerical mode the
+ * reference's pinned torch 1.10 (allow_tf32 = True by default, requirements.txt:19) used for these fp32 nn.Linear
+ * layers.  Needs 16-byte aligned bases and lda/ldb % 4 == 0; other shapes go to nv_sgemm. */
+int nv_gemm_tf32(const float* A, int64_t lda, int ta, const float* B, int64_t ldb, int tb, float* C, int64_t ldc,
+                 const float* bias, int M, int N, int K, int accumulate, void* stream);
 int nv_layernorm_fwd(const float* x, int64_t ldx, const float* gamma, const float* beta, const float* addend, int64_t ldadd,
                      float* y, int64_t ldy, float* mean, float* rstd, int R, int D, float eps, void* stream);
 int nv_layernorm_bwd_partials(void);

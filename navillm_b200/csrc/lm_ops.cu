@@ -163,14 +163,23 @@ __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_bwd_kernel(
 }
 
 // dst[j] = bf16(dst[j] + sum_p partial[p, j])   (accumulate = 1)   or   bf16(sum)   (accumulate = 0)
-__global__ void colsum_accum_bf16_kernel(const float* __restrict__ partial, int P, int D,
-                                         __nv_bfloat16* __restrict__ dst, int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= D) return;
+// Block = 32 columns x 8 row groups (a 16-block launch with one thread per column left the ~10 MB of partials
+// to 4096 threads: 41 us); fixed summation order, so the result is deterministic.
+__global__ void __launch_bounds__(256) colsum_accum_bf16_kernel(const float* __restrict__ partial, int P, int D,
+                                                                __nv_bfloat16* __restrict__ dst, int accumulate) {
+  __shared__ float red[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += partial[(int64_t)p * D + j];
-  if (accumulate) s += __bfloat162float(dst[j]);
-  dst[j] = __float2bfloat16_rn(s);
+  if (j < D)
+    for (int p = threadIdx.y; p < P; p += 8) s += partial[(int64_t)p * D + j];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < D) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) s += red[y][threadIdx.x];
+    if (accumulate) s += __bfloat162float(dst[j]);
+    dst[j] = __float2bfloat16_rn(s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -520,7 +529,7 @@ int nv_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const float* rstd,
                                                        BF(dx), lddx, workspace, T, D);
   NV_LAUNCH_CHECK();
   if (dw) {
-    colsum_accum_bf16_kernel<<<(D + 255) / 256, 256, 0, S_(stream)>>>(workspace, P, D, BF(dw), accumulate_dw);
+    colsum_accum_bf16_kernel<<<(D + 31) / 32, dim3(32, 8), 0, S_(stream)>>>(workspace, P, D, BF(dw), accumulate_dw);
     NV_LAUNCH_CHECK();
   }
   return NV_OK;

@@ -170,14 +170,21 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
   for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) partial[(int64_t)blockIdx.x * 2 * D + i] = acc[i];
 }
 
-// dst[j] (+)= sum_p src[p*stride + j]
-__global__ void colsum_f32_kernel(const float* __restrict__ src, int64_t stride, int P, int D, float* __restrict__ dst,
-                                  int accumulate) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= D) return;
+// dst[j] (+)= sum_p src[p*stride + j]     block = 32 columns x 8 row groups, fixed summation order
+__global__ void __launch_bounds__(256) colsum_f32_kernel(const float* __restrict__ src, int64_t stride, int P, int D,
+                                                         float* __restrict__ dst, int accumulate) {
+  __shared__ float red[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
   float s = 0.f;
-  for (int p = 0; p < P; ++p) s += src[(int64_t)p * stride + j];
-  dst[j] = accumulate ? dst[j] + s : s;
+  if (j < D)
+    for (int p = threadIdx.y; p < P; p += 8) s += src[(int64_t)p * stride + j];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < D) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) s += red[y][threadIdx.x];
+    dst[j] = accumulate ? dst[j] + s : s;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -423,11 +430,11 @@ int nv_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, const floa
                                                                      accumulate_dx, workspace, R, D);
   NV_LAUNCH_CHECK();
   if (dgamma) {
-    colsum_f32_kernel<<<(D + 255) / 256, 256, 0, S_(stream)>>>(workspace, 2 * D, P, D, dgamma, 1);
+    colsum_f32_kernel<<<(D + 31) / 32, dim3(32, 8), 0, S_(stream)>>>(workspace, 2 * D, P, D, dgamma, 1);
     NV_LAUNCH_CHECK();
   }
   if (dbeta) {
-    colsum_f32_kernel<<<(D + 255) / 256, 256, 0, S_(stream)>>>(workspace + D, 2 * D, P, D, dbeta, 1);
+    colsum_f32_kernel<<<(D + 31) / 32, dim3(32, 8), 0, S_(stream)>>>(workspace + D, 2 * D, P, D, dbeta, 1);
     NV_LAUNCH_CHECK();
   }
   return NV_OK;
@@ -435,7 +442,7 @@ int nv_layernorm_bwd(const float* x, int64_t ldx, const float* gamma, const floa
 
 int nv_colsum_f32(const float* src, int64_t ld, int R, int D, float* dst, int accumulate, void* stream) {
   if (D == 0) return NV_OK;
-  colsum_f32_kernel<<<(D + 255) / 256, 256, 0, S_(stream)>>>(src, ld, R, D, dst, accumulate);
+  colsum_f32_kernel<<<(D + 31) / 32, dim3(32, 8), 0, S_(stream)>>>(src, ld, R, D, dst, accumulate);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -5,6 +5,8 @@ launches on the current stream.  Nothing falls back to torch math.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -277,6 +279,20 @@ def _f32_2d(t: torch.Tensor, name: str) -> None:
         raise ValueError(f"{name}: expected a 2-D fp32 CUDA tensor with unit inner stride, got {t.dtype} {tuple(t.shape)} {t.stride()}")
 
 
+# Numerical mode of the fp32 panorama-encoder GEMMs: "tf32" = tcgen05 kind::tf32 (what the reference's pinned
+# torch 1.10 did by default on Ampere+: torch.backends.cuda.matmul.allow_tf32 = True), "fp32" = exact CUDA-core sgemm.
+_PANO_PRECISION = os.environ.get("NAVILLM_PANO_PRECISION", "tf32")
+
+
+def set_pano_precision(mode: str) -> str:
+    """Select "tf32" (default) or "fp32" for ops.sgemm; returns the previous mode."""
+    global _PANO_PRECISION
+    if mode not in ("tf32", "fp32"):
+        raise ValueError(f"pano precision must be 'tf32' or 'fp32', got {mode!r}")
+    prev, _PANO_PRECISION = _PANO_PRECISION, mode
+    return prev
+
+
 def sgemm(a, b, *, ta=False, tb=False, bias=None, out=None, accumulate=False):
     """C = op(A)·op(B) (+bias).  a: [M,K] (ta=False) / [K,M];  b: [N,K] (tb=False, nn.Linear weight) / [K,N]."""
     _f32_2d(a, "a"); _f32_2d(b, "b")
@@ -287,9 +303,12 @@ def sgemm(a, b, *, ta=False, tb=False, bias=None, out=None, accumulate=False):
         assert not accumulate
         out = torch.empty((M, N), dtype=f32_t, device=a.device)
     _f32_2d(out, "out")
-    check(_lib.load().nv_sgemm(ptr(a), i64(a.stride(0)), i32(ta), ptr(b), i64(b.stride(0)), i32(tb), ptr(out),
-                               i64(out.stride(0)), ptr(bias), i32(M), i32(N), i32(K), i32(accumulate), stream_ptr()),
-          "nv_sgemm")
+    # tensor-core path when TMA can address the operands (16-byte bases, row strides % 4) and the problem is not tiny
+    tc = (_PANO_PRECISION == "tf32" and K >= 32 and a.stride(0) % 4 == 0 and b.stride(0) % 4 == 0
+          and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0)
+    fn, name = (_lib.load().nv_gemm_tf32, "nv_gemm_tf32") if tc else (_lib.load().nv_sgemm, "nv_sgemm")
+    check(fn(ptr(a), i64(a.stride(0)), i32(ta), ptr(b), i64(b.stride(0)), i32(tb), ptr(out),
+             i64(out.stride(0)), ptr(bias), i32(M), i32(N), i32(K), i32(accumulate), stream_ptr()), name)
     return out
 
 

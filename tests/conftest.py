@@ -25,3 +25,13 @@ def cuda_dev():
     if not torch.cuda.is_available():
         pytest.fail("GPU test selected but torch.cuda.is_available() is False (no CPU fallback exists)")
     return torch.device("cuda:0")
+
+
+@pytest.fixture(params=["fp32", "tf32"])
+def pano_precision(request):
+    """Runs a GPU test in both numerical modes of the fp32 panorama-encoder GEMMs (navillm_b200.ops.set_pano_precision):
+    exact CUDA-core fp32 and the product default, tcgen05 kind::tf32."""
+    from navillm_b200 import ops
+    prev = ops.set_pano_precision(request.param)
+    yield request.param
+    ops.set_pano_precision(prev)

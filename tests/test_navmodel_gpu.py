@@ -5,7 +5,9 @@
 bf16 tolerance, stated: `truth` = golden fp32 run of the reference (nav_fp32.pt; same seeds, weights before
 bf16 rounding); the reference's own bf16 run deviates from it by e_ref.  The CUDA path, loaded with the bf16
 golden weights, must satisfy |cuda - ref_bf16| <= 3 * |ref_bf16 - truth|_max + 2e-2 * scale  for logits/losses
-and gradient tensors (scale = max|ref|).  fp32 parts (pano encoder outputs, fuse_embeds) must agree to 1e-4.
+and gradient tensors (scale = max|ref|).  fp32 parts (pano encoder outputs, fuse_embeds) must agree to 1e-4 with the
+exact-fp32 panorama GEMMs and to 4e-3 with the default tcgen05 kind::tf32 GEMMs (10-bit-mantissa operands, the mode
+the reference's pinned torch 1.10 used on Ampere+; see tests/test_pano_gpu.py).
 """
 import sys
 import types
@@ -62,7 +64,8 @@ def check(name, mine, ref, truth, k=3.0, floor=2e-2):
     assert e <= k * e_ref + floor * scale, f"{name}: |cuda-ref|={e:.4g} > {k}*{e_ref:.4g} + {floor}*{scale:.3g}"
 
 
-def test_navmodel_all_modes_match_reference(cuda_dev):
+def test_navmodel_all_modes_match_reference(cuda_dev, pano_precision):
+    tol32 = 1e-4 if pano_precision == "fp32" else 4e-3
     g = torch.load(GOLD / "nav_amp_bf16.pt", weights_only=False)
     t = torch.load(GOLD / "nav_fp32.pt", weights_only=False)
     model, tok = build_model(g, cuda_dev)
@@ -72,7 +75,7 @@ def test_navmodel_all_modes_match_reference(cuda_dev):
     pano = model("panorama", to_dev(dict(g["pano_in"]), cuda_dev))
     for k in ("pano_embeds", "obj_embeds"):
         ref = g["pano_out"][k]
-        assert (pano[k].detach().cpu() - ref).abs().max().item() <= 1e-4 * ref.abs().max().item(), k
+        assert (pano[k].detach().cpu() - ref).abs().max().item() <= tol32 * ref.abs().max().item(), k
     assert torch.equal(pano["pano_masks"].cpu(), g["pano_out"]["pano_masks"])
     assert torch.equal(pano["obj_masks"].cpu(), g["pano_out"]["obj_masks"])
 
@@ -85,7 +88,7 @@ def test_navmodel_all_modes_match_reference(cuda_dev):
     nav = model("navigation", nav_in)
     check("fuse_logits", nav["fuse_logits"].detach(), g["nav_out"]["fuse_logits"], t["nav_out"]["fuse_logits"])
     ref_fe = g["nav_out"]["fuse_embeds"]
-    assert (nav["fuse_embeds"].cpu() - ref_fe).abs().max().item() <= 1e-4 * ref_fe.abs().max().item()
+    assert (nav["fuse_embeds"].cpu() - ref_fe).abs().max().item() <= tol32 * ref_fe.abs().max().item()
     loss = F.cross_entropy(nav["fuse_logits"].float(), g["targets"].to(cuda_dev), reduction="sum", ignore_index=-100) / B
     check("nav loss", loss.detach(), g["nav_out"]["loss"], t["nav_out"]["loss"])
     loss.backward()
