@@ -158,12 +158,12 @@ struct TileRing {
   }
 };
 
-__device__ __forceinline__ void tile_coords2(uint32_t tile, uint32_t num_m, uint32_t num_n, uint32_t& m_blk,
-                                             uint32_t& n_blk) {
-  const uint32_t group_size = G2_GROUP_M * num_n;
+__device__ __forceinline__ void tile_coords2(uint32_t tile, uint32_t num_m, uint32_t num_n, uint32_t group_m,
+                                             uint32_t& m_blk, uint32_t& n_blk) {
+  const uint32_t group_size = group_m * num_n;
   const uint32_t g = tile / group_size;
-  const uint32_t first_m = g * G2_GROUP_M;
-  const uint32_t gm = min(num_m - first_m, G2_GROUP_M);
+  const uint32_t first_m = g * group_m;
+  const uint32_t gm = min(num_m - first_m, group_m);
   const uint32_t r = tile - g * group_size;
   m_blk = first_m + r % gm;
   n_blk = r / gm;
@@ -196,7 +196,8 @@ template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                        void* __restrict__ Cout, int64_t ldc, const __nv_bfloat16* __restrict__ addend, int64_t ld_add,
-                       uint32_t M, uint32_t N, uint32_t K, uint32_t flags, EpiAux ea, uint32_t* __restrict__ tile_counter) {
+                       uint32_t M, uint32_t N, uint32_t K, uint32_t flags, EpiAux ea, uint32_t* __restrict__ tile_counter,
+                       uint32_t group_m) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -262,7 +263,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                  : (leader ? ring.claim(tile_counter, num_tiles + num_clusters) : ring.take(false, lane));
       if (tile >= num_tiles) break;
       uint32_t m_blk, n_blk;
-      tile_coords2(tile, num_m, num_n, m_blk, n_blk);
+      tile_coords2(tile, num_m, num_n, group_m, m_blk, n_blk);
       const int32_t m0 = m_blk * 2 * G2_BM + rank * G2_BM;    // this CTA's A rows
       // this CTA's half of the B tile (SWIGLU: CTA 0 stages gate rows n.., CTA 1 the matching up rows F + n..)
       const int32_t n0 = (EPI == EPI_SWIGLU) ? (int32_t)(n_blk * 128 + rank * ea.F) : (int32_t)(n_blk * G2_BN + rank * G2_BNH);
@@ -334,7 +335,7 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
       const uint32_t tile = dyn ? ring.take(leader, lane) : cluster_id + iter * num_clusters;
       if (tile >= num_tiles) break;
       uint32_t m_blk, n_blk;
-      tile_coords2(tile, num_m, num_n, m_blk, n_blk);
+      tile_coords2(tile, num_m, num_n, group_m, m_blk, n_blk);
       const uint32_t acc = iter & 1, acc_phase = (iter >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
@@ -565,8 +566,18 @@ static int launch_gemm_2cta(const CUtensorMap& ta, const CUtensorMap& tb, void* 
   uint32_t* counter = nullptr;
   int rc = tile_counter_for(stream, &counter);
   if (rc) return rc;
+  // Rasterisation group (pair-tile rows swept together across N).  Measured DRAM reads per launch at T = 10.4k tokens
+  // (ncu, tools/gemm_raster.sh): K = 4096 projections 0.40 GB with 16 rows vs 0.68 GB with 8 (operand panels are
+  // small, a taller group reuses each B panel more); K >= 11008 problems 2.4 GB with 8 vs 2.7 GB with 16 (the
+  // A panels of a 16-row group no longer fit the L2 next to the streamed B panels).
+  static int group_env = -1;
+  if (group_env < 0) {
+    const char* e = getenv("NV_GEMM_GROUP_M");   // rasterisation experiments
+    group_env = (e && atoi(e) > 0) ? atoi(e) : 0;
+  }
+  const int group_m = group_env ? group_env : (K <= 8192 ? 2 * (int)G2_GROUP_M : (int)G2_GROUP_M);
   kern<<<clusters * 2, G2_THREADS, G2_DYN_BYTES, stream>>>(ta, tb, C, ldc, reinterpret_cast<const __nv_bfloat16*>(addend),
-                                                            ld_add, M, N, K, flags, ea, counter);
+                                                            ld_add, M, N, K, flags, ea, counter, (uint32_t)group_m);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -32,6 +32,9 @@ def main():
     ap.add_argument("--tokens", type=int, default=16384)
     ap.add_argument("--json", type=str, default="")
     ap.add_argument("--no-cublas", action="store_true")
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--only-512", action="store_true", help="time only the CTA-pair kernel")
     a = ap.parse_args()
     T = a.tokens
     dev = torch.device("cuda:0")
@@ -56,8 +59,8 @@ def main():
         C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
         flops = 2.0 * M * N * K
         res = {"name": name, "M": M, "N": N, "K": K}
-        for bn in (256, 512):
-            ms = timeit(lambda: ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=C, block_n=bn))
+        for bn in ((512,) if a.only_512 else (256, 512)):
+            ms = timeit(lambda: ops.gemm(A, B, a_mn=a_mn, b_mn=b_mn, out=C, block_n=bn), iters=a.iters, warmup=a.warmup)
             res[f"nv_bn{bn}_ms"] = ms
             res[f"nv_bn{bn}_tflops"] = flops / ms / 1e9
         if not a.no_cublas:
