@@ -68,26 +68,58 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* _
   unpack8d(*reinterpret_cast<const uint4*>(q + (int64_t)b * ldq + h * 128 + hl * 8), qf);
   const float sl2 = scale * 1.4426950408889634f;
   float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int j0 = w * 2; j0 < n; j0 += 8) {
-    const int j = j0 + half;
-    const bool ok = j < n;
-    float kf[8], vf[8];
-    float s = 0.f;
-    if (ok) {
-      const int64_t off = ((int64_t)b * Smax + j) * HD + h * 128 + hl * 8;
-      unpack8d(*reinterpret_cast<const uint4*>(kc + off), kf);
-      unpack8d(*reinterpret_cast<const uint4*>(vc + off), vf);
+  // A warp takes 8 consecutive keys per iteration (4 per half-warp): eight 16-byte loads per lane are in flight
+  // before the first use, which is what a latency-bound streaming loop needs (one key per half-warp and
+  // iteration kept ~1 MB in flight chip-wide and ran at 35 us for 52 MB of cache).
+  constexpr int KPI = 4;
+  for (int j0 = w * 2 * KPI; j0 < n; j0 += 8 * KPI) {
+    const int jb = j0 + half * KPI;
+    uint4 kraw[KPI], vraw[KPI];
+#pragma unroll
+    for (int u = 0; u < KPI; ++u) {
+      if (jb + u < n) {
+        const int64_t off = ((int64_t)b * Smax + jb + u) * HD + h * 128 + hl * 8;
+        kraw[u] = *reinterpret_cast<const uint4*>(kc + off);
+        vraw[u] = *reinterpret_cast<const uint4*>(vc + off);
+      } else {
+        kraw[u] = make_uint4(0, 0, 0, 0);
+        vraw[u] = make_uint4(0, 0, 0, 0);
+      }
+    }
+    float sc[KPI];
+#pragma unroll
+    for (int u = 0; u < KPI; ++u) {
+      float kf[8];
+      unpack8d(kraw[u], kf);
+      float s = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) s += qf[i] * kf[i];
+      sc[u] = s;
     }
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);   // reduce inside the half-warp
-    if (ok) {
-      const float mn = fmaxf(m, s);
-      const float a = exp2f((m - mn) * sl2), p = exp2f((s - mn) * sl2);
-      l = l * a + p;
+    for (int o = 8; o > 0; o >>= 1)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = acc[i] * a + p * vf[i];
+      for (int u = 0; u < KPI; ++u) sc[u] += __shfl_xor_sync(0xffffffffu, sc[u], o);   // reduce inside the half-warp
+    float mn = m;
+#pragma unroll
+    for (int u = 0; u < KPI; ++u)
+      if (jb + u < n) mn = fmaxf(mn, sc[u]);
+    if (mn != -INFINITY) {
+      const float a = exp2f((m - mn) * sl2);
+      l *= a;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= a;
+#pragma unroll
+      for (int u = 0; u < KPI; ++u) {
+        if (jb + u < n) {
+          const float p = exp2f((sc[u] - mn) * sl2);
+          float vf[8];
+          unpack8d(vraw[u], vf);
+          l += p;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) acc[i] += p * vf[i];
+        }
+      }
       m = mn;
     }
   }
@@ -126,37 +158,65 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* _
 
 // next[b] = finished[b] ? pad_id : argmax_c logits[b,c] over non-special columns (first index wins ties, like
 // torch.argmax); finished[b] |= next == eos (when stop_on_eos).  One CTA per row.
-__global__ void __launch_bounds__(256) argmax_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int V,
-                                                     const int* __restrict__ special, int n_special,
-                                                     int* __restrict__ finished, int eos_id, int pad_id, int stop_on_eos,
-                                                     int* __restrict__ next) {
-  __shared__ float sv[256];
-  __shared__ int si[256];
+__global__ void __launch_bounds__(1024) argmax_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int V,
+                                                      const int* __restrict__ special, int n_special,
+                                                      int* __restrict__ finished, int eos_id, int pad_id, int stop_on_eos,
+                                                      int* __restrict__ next) {
+  __shared__ float sv[32];
+  __shared__ int si[32];
+  __shared__ int s_special[64];
   const int b = blockIdx.x;
+  const int ns = min(n_special, 64);
+  if (threadIdx.x < ns) s_special[threadIdx.x] = special[threadIdx.x];
+  __syncthreads();
   float best = -INFINITY;
   int bi = V;
-  for (int c = threadIdx.x; c < V; c += blockDim.x) {
-    bool sp = false;
-    for (int s = 0; s < n_special; ++s) sp |= (special[s] == c);
-    if (sp) continue;
-    const float v = __bfloat162float(logits[(int64_t)b * ld + c]);
-    if (v > best) { best = v; bi = c; }   // strided scan keeps the smallest index per thread on ties
-  }
-  sv[threadIdx.x] = best; si[threadIdx.x] = bi;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) {
-      const float v2 = sv[threadIdx.x + o];
-      const int i2 = si[threadIdx.x + o];
-      if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) { sv[threadIdx.x] = v2; si[threadIdx.x] = i2; }
+  const __nv_bfloat16* row = logits + (int64_t)b * ld;
+  const bool vec_ok = (ld & 7) == 0;                       // 16-byte aligned rows
+  const int nvec = vec_ok ? (V >> 3) : 0;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float f[8];
+    unpack8d(*reinterpret_cast<const uint4*>(row + v * 8), f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = v * 8 + i;
+      bool sp = false;
+      for (int s = 0; s < ns; ++s) sp |= (s_special[s] == c);
+      if (!sp && f[i] > best) { best = f[i]; bi = c; }     // ascending scan keeps the smallest index per thread on ties
     }
-    __syncthreads();
   }
-  if (threadIdx.x == 0) {
-    int tok = si[0];
-    if (finished[b]) tok = pad_id;
-    else if (stop_on_eos && tok == eos_id) finished[b] = 1;
-    next[b] = tok;
+  for (int c = nvec * 8 + threadIdx.x; c < V; c += blockDim.x) {
+    bool sp = false;
+    for (int s = 0; s < ns; ++s) sp |= (s_special[s] == c);
+    const float v = __bfloat162float(row[c]);
+    if (!sp && (v > best || (v == best && c < bi))) { best = v; bi = c; }
+  }
+  // warp then CTA reduction; ties -> smallest index (torch.argmax returns the first maximal element)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (v2 > best || (v2 == best && i2 < bi)) { best = v2; bi = i2; }
+  }
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) { sv[w] = best; si[w] = bi; }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    best = lane < nw ? sv[lane] : -INFINITY;
+    bi = lane < nw ? si[lane] : V;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float v2 = __shfl_xor_sync(0xffffffffu, best, o);
+      const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (v2 > best || (v2 == best && i2 < bi)) { best = v2; bi = i2; }
+    }
+    if (lane == 0) {
+      int tok = bi;
+      if (finished[b]) tok = pad_id;
+      else if (stop_on_eos && tok == eos_id) finished[b] = 1;
+      next[b] = tok;
+    }
   }
 }
 
@@ -207,7 +267,7 @@ int nv_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* v
 int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id,
                      int pad_id, int stop_on_eos, int* next, int B, void* stream) {
   if (B == 0) return NV_OK;
-  argmax_kernel<<<B, 256, 0, S_(stream)>>>(CBF(logits), ld, V, special, n_special, finished, eos_id, pad_id, stop_on_eos, next);
+  argmax_kernel<<<B, 1024, 0, S_(stream)>>>(CBF(logits), ld, V, special, n_special, finished, eos_id, pad_id, stop_on_eos, next);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -15,6 +15,7 @@ PyTorch is used for device memory only.  There is no CPU path.
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -22,6 +23,10 @@ import torch
 import torch.nn as nn
 
 from . import ops
+
+# decode GEMMs: 0 = swap-AB skinny kernel for batches <= 16 (csrc/gemm_skinny.cu, default); 128 / 32 = column-tile
+# width of the general kernel (always used for 16 < batch <= 128)
+DECODE_BLOCK_N = int(os.environ.get("NAVILLM_DECODE_BLOCK_N", "0"))
 
 bf16 = torch.bfloat16
 
@@ -345,19 +350,23 @@ class LlamaCore:
         [B, D] before the final RMSNorm."""
         d = self.d
         H, D = d.n_heads, d.hidden
-        # M <= 128 is HBM-bound weight streaming.  Measured on B200 (tools/decode_bench.py, C3): 128-column tiles
-        # 5.9 ms/token; 32-column tiles (more CTAs for the N = 4096 projections) 8.8-12.2 ms/token -- re-filling the
-        # (mostly zero) 128-row activation tile per k-block costs more than the extra CTAs gain.  A swap-AB /
-        # split-K skinny kernel is the planned fix; until then 128-column tiles.
+        # M <= 128 is HBM-bound weight streaming.  Batches <= 16 use the swap-AB cluster-split-K kernel; the general
+        # kernel with 128-column tiles (activations on the UMMA M side) leaves most SMs idle on the 4096-wide
+        # projections (32 tiles) and re-stages a mostly-zero 128-row activation tile per k-block.
+        bn = DECODE_BLOCK_N
+        if bn == 0 and x.shape[0] <= 16:
+            lin = lambda a, w, addend=None: ops.gemm_skinny(a, w, addend=addend)
+        else:
+            lin = lambda a, w, addend=None: ops.gemm(a, w, addend=addend, block_n=bn or 128)
         for l, lyr in enumerate(self.model.layers):
             xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
-            qkv = ops.gemm(xn, self.wqkv[l], block_n=128)
+            qkv = lin(xn, self.wqkv[l])
             ops.rope_(qkv, lens, self.cos, self.sin, 2 * H, d.head_dim)
             ops.kv_append(qkv, lens, kc[l], vc[l])
             ao = ops.decode_attn(qkv, kc[l], vc[l], lens, H)
-            xm = ops.gemm(ao, self.wo[l], addend=x, block_n=128)
+            xm = lin(ao, self.wo[l], x)
             xn2, _ = ops.rmsnorm_fwd(xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
-            gu = ops.gemm(xn2, self.wgu[l], block_n=128)
+            gu = lin(xn2, self.wgu[l])
             h = ops.swiglu_fwd(gu)
-            x = ops.gemm(h, self.wd[l], addend=xm, block_n=128)
+            x = lin(h, self.wd[l], xm)
         return x

@@ -21,6 +21,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from . import llama as llama_mod
 from . import ops
 from .llama import FlatParams, LlamaCore, LlamaDims, LlamaModelParams, _Linear, init_llama_params_
 from .tokenizer import SPECIAL_TOKENS, HFTokenizerAdapter, SyntheticTokenizer
@@ -396,7 +397,10 @@ class ModifiedLlamaForCausalLM(nn.Module):
 
         def head(h_rows):
             hn, _ = ops.rmsnorm_fwd(h_rows, self.model.norm.weight.data, d.rms_eps)
-            ops.gemm(hn, self.lm_head.weight.data, out=logits, block_n=128)
+            if B <= 16 and llama_mod.DECODE_BLOCK_N == 0:
+                ops.gemm_skinny(hn, self.lm_head.weight.data, out=logits)
+            else:
+                ops.gemm(hn, self.lm_head.weight.data, out=logits, block_n=128)
 
         trie_state = [None]
 

@@ -469,6 +469,27 @@ def _timed(fn, flops, nbytes):
     return r
 
 
+def gemm_skinny(x: torch.Tensor, w: torch.Tensor, *, addend: torch.Tensor | None = None,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+    """Decode-step linear: x [M<=16, K] bf16, w [N, K] bf16 (nn.Linear weight) -> bf16 [M, N] (+ addend)."""
+    _rowmajor(x, "x"); _rowmajor(w, "w")
+    assert x.dtype == bf16 and w.dtype == bf16
+    M, K = x.shape
+    N = w.shape[0]
+    if w.shape[1] != K or M > 16:
+        raise ValueError(f"gemm_skinny: x {tuple(x.shape)} w {tuple(w.shape)} (needs M <= 16 and matching K)")
+    if out is None:
+        out = torch.empty((M, N), dtype=bf16, device=x.device)
+    _rowmajor(out, "out")
+    if addend is not None:
+        _rowmajor(addend, "addend")
+        assert addend.shape == (M, N) and addend.dtype == bf16
+    check(_lib.load().nv_gemm_skinny_bf16(ptr(x), i64(x.stride(0)), ptr(w), i64(w.stride(0)), ptr(out), i64(out.stride(0)),
+                                          ptr(addend), i64(addend.stride(0) if addend is not None else 0),
+                                          i32(M), i32(N), i32(K), stream_ptr()), "nv_gemm_skinny_bf16")
+    return out
+
+
 def gemm_swiglu(x, wgu, *, gu=None, h=None, keep_gu=True):
     """gu = x·Wgu^T ([T,2F]: gate | up) and h = silu(gate)*up ([T,F]) in ONE kernel (SwiGLU epilogue)."""
     _rowmajor(x, "x"); _rowmajor(wgu, "wgu")

@@ -116,3 +116,25 @@ def test_fused_epilogues_are_bit_identical_to_unfused(cuda_dev):
     q_u = ops.gemm(x, wqkv)
     ops.rope_(q_u, pos, cos_t, sin_t, 2 * H)
     assert torch.equal(q_f, q_u)
+
+
+@pytest.mark.parametrize("M", [1, 8, 16])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (12288, 4096), (22016, 4096), (4096, 11008), (32006, 4096), (200, 72), (136, 520)])
+@pytest.mark.parametrize("with_add", [False, True])
+def test_skinny_swap_ab_gemm(cuda_dev, M, N, K, with_add):
+    """Decode-step kernel (csrc/gemm_skinny.cu): same contract and tolerance as the general GEMM; the K range is
+    split over a cluster, so only the fp32 accumulation order differs."""
+    from navillm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M * 11 + N + K)
+    x = torch.randn(M, K, generator=g).to(cuda_dev, torch.bfloat16)
+    w = (torch.randn(N, K, generator=g) * 0.05).to(cuda_dev, torch.bfloat16)
+    add = torch.randn(M, N, generator=g).to(cuda_dev, torch.bfloat16) if with_add else None
+    out = ops.gemm_skinny(x, w, addend=add)
+    torch.cuda.synchronize()
+    ref = (x.float() @ w.float().t()).to(torch.bfloat16).float()
+    if with_add:
+        ref = (ref + add.float()).to(torch.bfloat16).float()
+    torch.testing.assert_close(out.float(), ref, rtol=1.6e-2, atol=2e-2)
+    # and against the general kernel: identical up to accumulation order (<= 2 bf16 ulp: accumulator rounding, then the rounded sum with the addend)
+    gen = ops.gemm(x, w, addend=add, block_n=128)
+    torch.testing.assert_close(out.float(), gen.float(), rtol=1.6e-2, atol=2e-2)
