@@ -70,6 +70,12 @@ int nv_gemm_rope_bf16(const void* x, int64_t ldx, const void* W, int64_t ldw, vo
 int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o, int64_t ldo,
                 float* lse, const int* cu_seqlens, int B, int T, int H, int head_dim, int total_qblocks, float scale,
                 void* stream);
+/* Suffix attention over a KV cache: queries = packed new rows (cu_seqlens), keys/values of sequence b = rows
+ * kv_start[b] .. +kv_len[b] of the cache tensors (Tkv rows, zero-initialised); query i of b sees keys <= kv_len[b] -
+ * q_len[b] + i.  Same kernel as nv_attn_fwd (which is the kv_len == q_len, kv_start == cu_seqlens case). */
+int nv_attn_fwd_kv(const void* q, int64_t ldq, const void* kcache, int64_t ldk, const void* vcache, int64_t ldv, void* o,
+                   int64_t ldo, float* lse, const int* cu_seqlens, const int* kv_start, const int* kv_len, int B, int Tq,
+                   int Tkv, int H, int head_dim, int total_qblocks, float scale, void* stream);
 int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, const void* o,
                 int64_t ldo, const void* dout, int64_t lddo, const float* lse, float* dvec, void* dq, int64_t lddq,
                 void* dk, int64_t lddk, void* dv, int64_t lddv, const int* cu_seqlens, int B, int T, int H, int head_dim,
@@ -145,6 +151,11 @@ int nv_kv_store_prefill(const void* qkv, int64_t ld, const int* cu_seqlens, void
                         int Smax, int HD, void* stream);
 int nv_kv_append(const void* qkv, int64_t ld, const int* lens, void* kcache, void* vcache, int B, int Smax, int HD,
                  void* stream);
+/* Cross-step prefix-KV reuse in rollouts (caller tasks/agents/mp3d_agent.py:660-726, prompt order
+ * tasks/agents/r2r.py:16-31): store the K/V of the NEW rows of each sequence after the cached[b] rows the cache already
+ * holds, then attend from the new rows over cached + new keys (nv_attn_fwd_kv). */
+int nv_kv_store_suffix(const void* qkv, int64_t ld, const int* cu_seqlens, const int* cached, void* kcache, void* vcache,
+                       int B, int T, int Smax, int HD, void* stream);
 int nv_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* vcache, const int* lens, void* out,
                    int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream);
 int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id,

@@ -40,11 +40,11 @@ struct AttnFwdSmem {
 
 // Map a flat block id to (sequence, 256-row query block); heavy (late) blocks are launched first.
 __device__ __forceinline__ bool locate_qblock(const int* __restrict__ cu, int B, uint32_t blk, int& seq_start,
-                                              int& seq_len, uint32_t& qblk) {
+                                              int& seq_len, uint32_t& qblk, int& seq_idx) {
   for (int b = 0; b < B; ++b) {
     const int s = cu[b], len = cu[b + 1] - s;
     const uint32_t nb = (len + ATT_QROWS - 1) / ATT_QROWS;
-    if (blk < nb) { seq_start = s; seq_len = len; qblk = blk; return true; }
+    if (blk < nb) { seq_start = s; seq_len = len; qblk = blk; seq_idx = b; return true; }
     blk -= nb;
   }
   return false;
@@ -53,7 +53,8 @@ __device__ __forceinline__ bool locate_qblock(const int* __restrict__ cu, int B,
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
                 const __grid_constant__ CUtensorMap tmap_v, __nv_bfloat16* __restrict__ O, int64_t ldo,
-                float* __restrict__ lse, const int* __restrict__ cu_seqlens, int B, int T, float scale) {
+                float* __restrict__ lse, const int* __restrict__ cu_seqlens, int B, int T, float scale,
+                const int* __restrict__ kv_start, const int* __restrict__ kv_len) {
   using L = AttnFwdSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -75,14 +76,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
   const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
   const uint32_t head = blockIdx.y;
 
-  int seq_start = 0, seq_len = 0;
+  int seq_start = 0, seq_len = 0, seq_idx = 0;
   uint32_t qblk = 0;
-  if (!locate_qblock(cu_seqlens, B, gridDim.x - 1 - blockIdx.x, seq_start, seq_len, qblk)) return;  // CTA-uniform
+  if (!locate_qblock(cu_seqlens, B, gridDim.x - 1 - blockIdx.x, seq_start, seq_len, qblk, seq_idx)) return;  // CTA-uniform
+  // Keys: by default the sequence's own rows (self-attention over the packed batch).  With kv_start / kv_len the
+  // keys of sequence b are rows kv_start[b] .. +kv_len[b] of the K/V tensors (a KV cache holding an already encoded
+  // prefix followed by the new rows) and the queries are its LAST seq_len positions: query i sees keys <= dk + i,
+  // dk = kv_len - seq_len.
+  const int kv0 = kv_start ? kv_start[seq_idx] : seq_start;
+  const uint32_t dk = kv_len ? (uint32_t)(kv_len[seq_idx] - seq_len) : 0u;
   const uint32_t q0 = qblk * ATT_QROWS;                         // first query row (inside the sequence)
   const bool tile1_on = (q0 + 128) < (uint32_t)seq_len;         // second tile has at least one real row
-  // key blocks: tile 0 sees blocks 0..2*qblk, tile 1 sees 0..2*qblk+1
-  const uint32_t n_blocks = tile1_on ? 2 * qblk + 2 : 2 * qblk + 1;
-  auto tile_on = [&](uint32_t t, uint32_t j) -> bool { return t == 0 ? (j <= 2 * qblk) : (tile1_on && j <= 2 * qblk + 1); };
+  // key blocks seen by a tile: 0 .. ceil((dk + last real row + 1) / 128) - 1   (dk = 0: 2*qblk+1 and 2*qblk+2)
+  const uint32_t nb0 = (dk + min(q0 + 128, (uint32_t)seq_len) + 127) / 128;
+  const uint32_t nb1 = tile1_on ? (dk + min(q0 + 256, (uint32_t)seq_len) + 127) / 128 : 0u;
+  const uint32_t n_blocks = max(nb0, nb1);
+  auto tile_on = [&](uint32_t t, uint32_t j) -> bool { return j < (t == 0 ? nb0 : nb1); };
   auto last_tile = [&](uint32_t j) -> uint32_t { return tile_on(1, j) ? 1u : 0u; };
   auto first_tile = [&](uint32_t j) -> uint32_t { return tile_on(0, j) ? 0u : 1u; };
 
@@ -117,7 +126,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     }
     __syncwarp();
     for (uint32_t j = 0; j < n_blocks; ++j) {
-      const int32_t krow0 = seq_start + j * 128;
+      const int32_t krow0 = kv0 + j * 128;
       mbar_wait(k_empty, (j & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(k_full, ATT_TILE_BYTES);
@@ -206,13 +215,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
     const uint32_t tmem_S = tmem_base + t * 128, tmem_O = tmem_base + 256 + t * 128;
     uint8_t* sPt = sP + t * ATT_TILE_BYTES;
     const float sl2 = scale * 1.4426950408889634f;
-    const uint32_t my_blocks = (t == 0) ? (2 * qblk + 1) : (tile1_on ? 2 * qblk + 2 : 0);
-    const uint32_t diag_blk = 2 * qblk + t;
+    const uint32_t my_blocks = (t == 0) ? nb0 : nb1;
+    const uint32_t vis0 = dk + q0 + t * 128;               // last key visible to the tile's first row
     float m_run = -INFINITY, l_run = 0.f;
     for (uint32_t j = 0; j < my_blocks; ++j) {
       mbar_wait(&s_full[t], j & 1);
       tc_fence_after();
-      const bool diag = (j == diag_blk);
+      const bool diag = (j * 128 + 127 > vis0);             // block holds keys that some row of the tile must not see
+      const int lim = (int)(vis0 + r) - (int)(j * 128);     // this row sees columns 0 .. lim of the block
       // whole S row -> registers (4 x 32 columns), one wait
       uint32_t s[128];
       tmem_ld_32x32b_x32(tmem_S + lane_off + 0, *reinterpret_cast<uint32_t(*)[32]>(&s[0]));
@@ -224,7 +234,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       float mx[4] = {m_run, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (uint32_t i = 0; i < 128; ++i)
-        if (!diag || i <= r) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[i]));
+        if (!diag || (int)i <= lim) mx[i & 3] = fmaxf(mx[i & 3], __uint_as_float(s[i]));
       const float m_new = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       const float alpha = exp2f((m_run - m_new) * sl2);
       const float mb = m_new * sl2;
@@ -234,8 +244,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
         float p0 = exp2f(__uint_as_float(s[i]) * sl2 - mb);
         float p1 = exp2f(__uint_as_float(s[i + 1]) * sl2 - mb);
         if (diag) {
-          if (i > r) p0 = 0.f;
-          if (i + 1 > r) p1 = 0.f;
+          if ((int)i > lim) p0 = 0.f;
+          if ((int)i + 1 > lim) p1 = 0.f;
         }
         // the row sum uses the bf16-rounded probabilities that the PV product actually consumes
         const uint32_t pk = pack_bf16x2(p0, p1);
@@ -309,9 +319,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
 // columns [h*128, (h+1)*128).  o: [T, H*128] bf16 (ldo).  lse: [H, T] fp32 or null.
 // cu_seqlens: device int32 [B+1]; total_qblocks = sum_b ceil(len_b / 128) (the host knows the lengths);
 // the kernel itself works on 256-row blocks: the grid is sized from an upper bound and surplus CTAs exit.
-extern "C" int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
-                           int64_t ldo, float* lse, const int* cu_seqlens, int B, int T, int H, int head_dim,
-                           int total_qblocks, float scale, void* stream) {
+static int attn_fwd_launch(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                           int64_t ldo, float* lse, const int* cu_seqlens, const int* kv_start, const int* kv_len, int B, int T,
+                           int Tkv, int H, int head_dim, int total_qblocks, float scale, void* stream) {
   using namespace nv;
   NV_REQUIRE(head_dim == 128, "nv_attn_fwd: head_dim must be 128 (got %d)", head_dim);
   NV_REQUIRE(B > 0 && T > 0 && H > 0 && total_qblocks > 0, "nv_attn_fwd: empty problem");
@@ -319,8 +329,8 @@ extern "C" int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_tmap_2d(&tq, q, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldq * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d(&tk, k, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldk * 2, 64, 128))) return rc;
-  if ((rc = make_tmap_2d(&tv, v, 2, (uint64_t)H * 128, (uint64_t)T, (uint64_t)ldv * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d(&tk, k, 2, (uint64_t)H * 128, (uint64_t)Tkv, (uint64_t)ldk * 2, 64, 128))) return rc;
+  if ((rc = make_tmap_2d(&tv, v, 2, (uint64_t)H * 128, (uint64_t)Tkv, (uint64_t)ldv * 2, 64, 128))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     NV_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnFwdSmem::DYN_BYTES));
@@ -330,7 +340,28 @@ extern "C" int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ld
   const int grid_x = (total_qblocks + B + 1) / 2;
   dim3 grid(grid_x, H);
   attn_fwd_kernel<<<grid, ATT_THREADS, AttnFwdSmem::DYN_BYTES, reinterpret_cast<cudaStream_t>(stream)>>>(
-      tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(o), ldo, lse, cu_seqlens, B, T, scale);
+      tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(o), ldo, lse, cu_seqlens, B, T, scale, kv_start, kv_len);
   NV_LAUNCH_CHECK();
   return NV_OK;
+}
+
+extern "C" int nv_attn_fwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, void* o,
+                           int64_t ldo, float* lse, const int* cu_seqlens, int B, int T, int H, int head_dim,
+                           int total_qblocks, float scale, void* stream) {
+  return attn_fwd_launch(q, ldq, k, ldk, v, ldv, o, ldo, lse, cu_seqlens, nullptr, nullptr, B, T, T, H, head_dim,
+                         total_qblocks, scale, stream);
+}
+
+// Suffix ("append") attention over a KV cache: the Tq packed query rows of sequence b (cu_seqlens) are the LAST
+// positions of a context whose keys/values are rows kv_start[b] .. kv_start[b] + kv_len[b] of the cache tensors
+// (Tkv rows in total; kv_len[b] >= query count, already holding the new rows' K/V).  Rows of the cache past kv_len
+// must be finite (allocate it zeroed): they are masked, but 0 * NaN would poison the P·V product.
+extern "C" int nv_attn_fwd_kv(const void* q, int64_t ldq, const void* kcache, int64_t ldk, const void* vcache, int64_t ldv,
+                              void* o, int64_t ldo, float* lse, const int* cu_seqlens, const int* kv_start,
+                              const int* kv_len, int B, int Tq, int Tkv, int H, int head_dim, int total_qblocks, float scale,
+                              void* stream) {
+  using namespace nv;
+  NV_REQUIRE(kv_start && kv_len, "nv_attn_fwd_kv: kv_start / kv_len are required");
+  return attn_fwd_launch(q, ldq, kcache, ldk, vcache, ldv, o, ldo, lse, cu_seqlens, kv_start, kv_len, B, Tq, Tkv, H,
+                         head_dim, total_qblocks, scale, stream);
 }

@@ -19,8 +19,8 @@ __device__ __forceinline__ void unpack8d(const uint4& u, float (&f)[8]) {
 // Copy the K and V column blocks of packed prefill rows into the cache: row t of sequence b at local
 // position p goes to cache[b, p, :].
 __global__ void kv_store_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t ld, const int* __restrict__ cu,
-                                        __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int Smax,
-                                        int HD) {
+                                        const int* __restrict__ offs, __nv_bfloat16* __restrict__ kc,
+                                        __nv_bfloat16* __restrict__ vc, int B, int Smax, int HD) {
   const int vecs = HD >> 3;
   const int T = cu[B];
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < (int64_t)T * vecs;
@@ -28,7 +28,7 @@ __global__ void kv_store_prefill_kernel(const __nv_bfloat16* __restrict__ qkv, i
     const int v = idx % vecs, t = idx / vecs;
     int b = 0;
     while (b + 1 < B && cu[b + 1] <= t) ++b;
-    const int p = t - cu[b];
+    const int p = t - cu[b] + (offs ? offs[b] : 0);          // offs: rows already cached for this sequence
     if (p >= Smax) continue;
     const int64_t dst = ((int64_t)b * Smax + p) * HD + v * 8;
     *reinterpret_cast<uint4*>(kc + dst) = *reinterpret_cast<const uint4*>(qkv + (int64_t)t * ld + HD + v * 8);
@@ -242,7 +242,21 @@ int nv_kv_store_prefill(const void* qkv, int64_t ld, const int* cu_seqlens, void
   int grid = (int)((work + 255) / 256);
   const int cap = sm_count() * 16;
   if (grid > cap) grid = cap;
-  kv_store_prefill_kernel<<<grid, 256, 0, S_(stream)>>>(CBF(qkv), ld, cu_seqlens, BF(kcache), BF(vcache), B, Smax, HD);
+  kv_store_prefill_kernel<<<grid, 256, 0, S_(stream)>>>(CBF(qkv), ld, cu_seqlens, nullptr, BF(kcache), BF(vcache), B, Smax, HD);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+// Same, appending after `cached[b]` rows that the cache already holds for sequence b (cross-step prefix reuse).
+int nv_kv_store_suffix(const void* qkv, int64_t ld, const int* cu_seqlens, const int* cached, void* kcache, void* vcache,
+                       int B, int T, int Smax, int HD, void* stream) {
+  if (T == 0) return NV_OK;
+  NV_REQUIRE((HD & 7) == 0 && (ld & 7) == 0 && cached, "nv_kv_store_suffix: alignment / null offsets");
+  const int64_t work = (int64_t)T * (HD >> 3);
+  int grid = (int)((work + 255) / 256);
+  const int cap = sm_count() * 16;
+  if (grid > cap) grid = cap;
+  kv_store_prefill_kernel<<<grid, 256, 0, S_(stream)>>>(CBF(qkv), ld, cu_seqlens, cached, BF(kcache), BF(vcache), B, Smax, HD);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -281,6 +281,43 @@ class LlamaCore:
         return x, ((saved, (pos, cu, list(seqlens))) if save else None)
 
     # -------------------------------------------------------------------------------------------------
+    def forward_suffix(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, q_lens, kc: List[torch.Tensor],
+                       vc: List[torch.Tensor], cached: torch.Tensor, kv_start: torch.Tensor, kv_len: torch.Tensor,
+                       out_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Inference-only forward of NEW rows on top of a per-layer KV cache that already holds an encoded prefix of
+        every sequence (cross-step prefix reuse).  x: [Tn, D] packed embeddings of the new tokens,
+        pos: their rotary positions, cu / q_lens: packing of the new rows, caches [B, Smax, D] (zero-initialised),
+        cached / kv_start / kv_len: int32 [B] on the device (rows already cached, first cache row of the sequence,
+        cached + new).  The new rows' K/V are appended to the cache; returns the residual stream ([Tn, D], or
+        [R, D] with ``out_rows``) before the final RMSNorm."""
+        d = self.d
+        H, D = d.n_heads, d.hidden
+        B, T = len(q_lens), x.shape[0]
+        last = d.n_layers - 1
+        fused = self.fused_epilogues and T >= 1024 and d.inter % 128 == 0 and d.hidden % 256 == 0
+        for l, lyr in enumerate(self.model.layers):
+            xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
+            if fused:
+                qkv = ops.gemm_rope(xn, self.wqkv[l], pos, self.cos, self.sin, 2 * D)
+            else:
+                qkv = ops.gemm(xn, self.wqkv[l])
+                ops.rope_(qkv, pos, self.cos, self.sin, 2 * H, d.head_dim)
+            ops.kv_store_suffix(qkv, cu, cached, kc[l], vc[l], B, T)
+            ao = ops.attn_fwd_kv(qkv[:, :D], kc[l], vc[l], cu, q_lens, kv_start, kv_len, H)
+            xin = x
+            if out_rows is not None and l == last:
+                ao = ops.gather_rows(ao, out_rows)
+                xin = ops.gather_rows(x, out_rows)
+            xm = ops.gemm(ao, self.wo[l], addend=xin)
+            xn2, _ = ops.rmsnorm_fwd(xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
+            if fused and xm.shape[0] >= 1024:
+                _, h = ops.gemm_swiglu(xn2, self.wgu[l], keep_gu=False)
+            else:
+                h = ops.swiglu_fwd(ops.gemm(xn2, self.wgu[l]))
+            x = ops.gemm(h, self.wd[l], addend=xm)
+        return x
+
+    # -------------------------------------------------------------------------------------------------
     def backward(self, dx: torch.Tensor, tape, layer_done=None) -> torch.Tensor:
         """dx: [T, D] bf16 gradient w.r.t. the forward's hidden output; ``tape`` from that forward (consumed).
         Accumulates every weight gradient in place (or OVERWRITES it when ``flat.overwrite_layer_grads`` is set

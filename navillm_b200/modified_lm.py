@@ -93,6 +93,40 @@ class PackedPrompt:
         self.flat_rows = flat_rows                                        # host copy (unpacking to [B,S])
 
 
+class PrefixKVCache:
+    """Per-rollout KV cache for cross-step prompt-prefix reuse (not in the reference).
+
+    In a navigation rollout the prompt of step t+1 repeats the prompt of step t up to the end of the history
+    (tasks/agents/r2r.py:16-31: instruction | (0) <hist> ... (t-1) <hist> | candidates | output hint), yet the
+    reference re-encodes it from scratch every step (tasks/agents/mp3d_agent.py:660-726).  With frozen weights
+    (evaluation / inference) the K/V of that prefix can be kept: each step encodes only the tokens after the longest
+    common token prefix with what the cache holds for the row.
+
+    Positions: the reference gives token j of a left-padded row the rotary position pad_b + j, and pad_b changes
+    from step to step.  Rotary attention depends on position DIFFERENCES only, so a row keeps the offset of its first
+    step for the whole rollout (``off``); results differ from a from-scratch forward only through bf16 rounding of
+    the cos/sin tables at different absolute positions (tests/test_prefix_reuse_gpu.py states the tolerance).
+
+    Contract: rows are identified by batch index; the <hist> vectors of a row are append-only across steps (the
+    reference's hist_vis lists are); call ``reset()`` when a new episode starts in a row."""
+
+    def __init__(self, lm: "ModifiedLlamaForCausalLM", batch_size: int, max_len: int = 2048):
+        lm._ensure()
+        dev, d = lm._device(), lm.dims
+        self.B, self.max_len = batch_size, max_len
+        # zero-initialised: rows past a sequence's length are masked in the attention kernel but must stay finite
+        self.kc = [torch.zeros((batch_size, max_len, d.hidden), dtype=bf16, device=dev) for _ in range(d.n_layers)]
+        self.vc = [torch.zeros((batch_size, max_len, d.hidden), dtype=bf16, device=dev) for _ in range(d.n_layers)]
+        self.ids: List[np.ndarray] = [np.zeros(0, dtype=np.int64) for _ in range(batch_size)]
+        self.off: List[Optional[int]] = [None] * batch_size
+        self.stats = {"steps": 0, "tokens": 0, "tokens_encoded": 0}
+
+    def reset(self, rows=None) -> None:
+        for b in (range(self.B) if rows is None else rows):
+            self.ids[b] = np.zeros(0, dtype=np.int64)
+            self.off[b] = None
+
+
 class _LMFn(torch.autograd.Function):
     """Differentiable boundary of the language model for a packed prompt.
 
@@ -315,6 +349,81 @@ class ModifiedLlamaForCausalLM(nn.Module):
         train = torch.is_grad_enabled() and self.training_enabled
         anchor = self._anchor.detach().requires_grad_(train)
         return _LMFn.apply(self, pp, vis, "rows", rows, train, anchor)
+
+    @torch.no_grad()
+    def hidden_rows_cached(self, input_ids: torch.Tensor, attention_mask: torch.Tensor, cand_vis: Optional[torch.Tensor],
+                           hist_vis: Optional[torch.Tensor], hist_counts, cache: PrefixKVCache) -> torch.Tensor:
+        """Inference twin of ``hidden_rows(pp, vis, pp.cls_rows)`` that encodes only the tokens after each row's
+        longest common prefix with ``cache`` (see PrefixKVCache).  cand_vis: [sum cand, D] in row-major token order;
+        hist_vis: [sum_b hist_counts[b], D] flattened sample-major (NavModel._flatten_hist).  Returns the final-
+        RMSNorm'ed hidden states at the <cls_1> tokens, [B, D] bf16."""
+        self._ensure()
+        dev, d = self._device(), self.dims
+        ids = input_ids.detach().cpu().numpy().astype(np.int64)
+        msk = attention_mask.detach().cpu().numpy().astype(bool)
+        B, S = ids.shape
+        if B != cache.B:
+            raise ValueError(f"prefix cache was built for batch {cache.B}, got {B} prompts")
+        cand_id, hist_id, cls_id = self.cand_token_id[0], self.hist_token_id[0], self.cls_token_id[0]
+        hist_base = np.concatenate([[0], np.cumsum(np.asarray(hist_counts, dtype=np.int64))])
+        tok_new, pos_new, vis_new, q_lens, cached, kv_len, cls_rows = [], [], [], [], [], [], []
+        n_cand_seen, t0 = 0, 0
+        n_cand_total = 0 if cand_vis is None else cand_vis.shape[0]
+        for b in range(B):
+            toks = ids[b][msk[b]]
+            L = int(toks.size)
+            if L == 0 or not msk[b, S - L:].all():
+                raise ValueError("prefix reuse needs left-padded prompts with at least one token")
+            if L > cache.max_len:
+                raise ValueError(f"prompt of {L} tokens exceeds the prefix cache length {cache.max_len}")
+            if cache.off[b] is None:
+                cache.off[b] = S - L                               # the row keeps this rotary offset for the rollout
+            old = cache.ids[b]
+            m = min(old.size, L - 1)                               # at least the last token is encoded
+            neq = np.flatnonzero(old[:m] != toks[:m])
+            n = int(neq[0]) if neq.size else m
+            cpos = np.flatnonzero(toks == cand_id)                 # candidates change every step: never reused
+            if cpos.size:
+                n = min(n, int(cpos[0]))
+            new = toks[n:]
+            is_h, is_c = new == hist_id, new == cand_id
+            h_before = int((toks[:n] == hist_id).sum())
+            vs = np.full(new.size, -1, dtype=np.int64)
+            vs[is_c] = n_cand_seen + np.arange(int(is_c.sum()))
+            vs[is_h] = n_cand_total + hist_base[b] + h_before + np.arange(int(is_h.sum()))
+            if h_before + int(is_h.sum()) != int(hist_counts[b]):
+                raise RuntimeError(f"row {b}: {h_before + int(is_h.sum())} <hist> tokens but {int(hist_counts[b])} hist_vis rows")
+            n_cand_seen += int(is_c.sum())
+            c = np.flatnonzero(new == cls_id)
+            if c.size != 1:
+                raise RuntimeError(f"expected one <cls_1> token after the reusable prefix of row {b}, found {c.size}")
+            cls_rows.append(t0 + int(c[0]))
+            tok_new.append(new); vis_new.append(vs)
+            pos_new.append(cache.off[b] + n + np.arange(new.size))
+            q_lens.append(int(new.size)); cached.append(n); kv_len.append(L)
+            t0 += int(new.size)
+            cache.ids[b] = toks.copy()
+        if n_cand_seen != n_cand_total:
+            raise RuntimeError(f"{n_cand_seen} <cand> tokens in the prompts but {n_cand_total} cand_vis rows")
+        cu = np.concatenate([[0], np.cumsum(q_lens)])
+        kv_start = np.arange(B, dtype=np.int64) * cache.max_len
+        parts = [np.concatenate(tok_new), np.concatenate(pos_new), cu, np.concatenate(vis_new), np.asarray(cls_rows),
+                 np.asarray(cached), kv_start, np.asarray(kv_len)]
+        host = np.concatenate([p.astype(np.int32) for p in parts])
+        dev_buf = torch.from_numpy(host).pin_memory().to(dev, non_blocking=True)
+        views, o = [], 0
+        for p in parts:
+            views.append(dev_buf[o:o + p.size]); o += p.size
+        tok_d, pos_d, cu_d, vis_d, cls_d, cached_d, kvs_d, kvl_d = views
+        vis_parts = [v.to(torch.float32) for v in (cand_vis, hist_vis) if v is not None and v.shape[0] > 0]
+        vis = None if not vis_parts else (vis_parts[0].contiguous() if len(vis_parts) == 1 else torch.cat(vis_parts, 0))
+        x = ops.embed_fwd(tok_d, self.model.embed_tokens.weight.data, vis_d if vis is not None else None, vis)
+        g = self.core.forward_suffix(x, pos_d, cu_d, q_lens, cache.kc, cache.vc, cached_d, kvs_d, kvl_d, out_rows=cls_d)
+        hn, _ = ops.rmsnorm_fwd(g, self.model.norm.weight.data, d.rms_eps)
+        cache.stats["steps"] += 1
+        cache.stats["tokens"] += int(sum(kv_len))
+        cache.stats["tokens_encoded"] += int(sum(q_lens))
+        return hn
 
     def lm_loss(self, pp: PackedPrompt, vis: Optional[torch.Tensor]) -> torch.Tensor:
         self._ensure()

@@ -370,11 +370,20 @@ class NavModel(nn.Module):
         # `text_input` (optional, not in the reference): an already tokenised TokenBatch for callers that keep
         # the prompt ids resident; otherwise tokenise on the host exactly like models/nav_model.py:211
         text = batch["text_input"] if batch["text_input"] is not None else self.lang_model.tokenize(batch["prompts"])
-        pp = PackedPrompt(text["input_ids"], text["attention_mask"], self.lang_model, dev)
-        vis = self.lang_model.cat_vis(cand_embeds, hist_vis_input, None, pp)
-        if pp.n_cls != B:
-            raise RuntimeError(f"expected one <cls_1> token per prompt, found {pp.n_cls} in {B} prompts")
-        h_cls = self.lang_model.hidden_rows(pp, vis, pp.cls_rows)
+        prefix_cache = kwargs.get("prefix_cache")
+        if prefix_cache is not None:
+            # evaluation rollouts (not in the reference): encode only what follows each row's cached prompt prefix
+            if torch.is_grad_enabled():
+                raise RuntimeError("prefix_cache is an inference feature: call under torch.no_grad() (weights must not change)")
+            hist_counts = [len(v) for v in (batch["hist_vis"] or [[] for _ in range(B)])]
+            h_cls = self.lang_model.hidden_rows_cached(text["input_ids"], text["attention_mask"], cand_embeds, hist_vis_input,
+                                                       hist_counts, prefix_cache)
+        else:
+            pp = PackedPrompt(text["input_ids"], text["attention_mask"], self.lang_model, dev)
+            vis = self.lang_model.cat_vis(cand_embeds, hist_vis_input, None, pp)
+            if pp.n_cls != B:
+                raise RuntimeError(f"expected one <cls_1> token per prompt, found {pp.n_cls} in {B} prompts")
+            h_cls = self.lang_model.hidden_rows(pp, vis, pp.cls_rows)
         fuse_logits = _HeadFn.apply(self.out_head[0], h_cls, self._idx(slot), B, G)
         return {"fuse_embeds": fuse.detach().view(B, G, D), "fuse_logits": fuse_logits}
 

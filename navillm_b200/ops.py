@@ -92,6 +92,32 @@ def attn_fwd(qkv: torch.Tensor, cu_seqlens: torch.Tensor, seqlens, n_heads: int,
     return out, lse
 
 
+def attn_fwd_kv(q: torch.Tensor, kcache: torch.Tensor, vcache: torch.Tensor, cu_q: torch.Tensor, q_lens, kv_start: torch.Tensor,
+                kv_len: torch.Tensor, n_heads: int, *, out: torch.Tensor | None = None, scale: float | None = None):
+    """Suffix attention over a KV cache (nv_attn_fwd_kv): q [Tq, >=H*128] bf16 view of the packed new rows (RoPE
+    applied), caches [B, Smax, H*128] bf16 (already holding the new rows' K/V, zero-initialised), kv_start / kv_len
+    int32 [B] on the device.  Query i of sequence b sees keys <= kv_len[b] - q_lens[b] + i.  Returns o [Tq, H*128]."""
+    _rowmajor(q, "q")
+    hd = 128
+    Tq = q.shape[0]
+    B = len(q_lens)
+    assert q.dtype == bf16 and kcache.dtype == bf16 and vcache.dtype == bf16 and kcache.is_contiguous() and vcache.is_contiguous()
+    assert kcache.dim() == 3 and kcache.shape[2] == n_heads * hd and kcache.shape == vcache.shape
+    for t in (cu_q, kv_start, kv_len):
+        assert t.dtype == torch.int32 and t.is_cuda
+    if out is None:
+        out = torch.empty((Tq, n_heads * hd), dtype=bf16, device=q.device)
+    if scale is None:
+        scale = hd ** -0.5
+    Tkv = kcache.shape[0] * kcache.shape[1]
+    ldk = kcache.shape[2]
+    check(_lib.load().nv_attn_fwd_kv(ptr(q), i64(q.stride(0)), ptr(kcache), i64(ldk), ptr(vcache), i64(ldk), ptr(out),
+                                     i64(out.stride(0)), ptr(None), ptr(cu_q), ptr(kv_start), ptr(kv_len), i32(B), i32(Tq),
+                                     i32(Tkv), i32(n_heads), i32(hd), i32(_qblocks(q_lens)), f32(scale), stream_ptr()),
+          "nv_attn_fwd_kv")
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
 # row-wise LM kernels (csrc/lm_ops.cu)
 # ---------------------------------------------------------------------------------------------------
@@ -420,6 +446,13 @@ def kv_store_prefill(qkv, cu, kc, vc, B, T):
     Smax, HD = kc.shape[1], kc.shape[2]
     check(_lib.load().nv_kv_store_prefill(ptr(qkv), i64(qkv.stride(0)), ptr(cu), ptr(kc), ptr(vc), i32(B), i32(T), i32(Smax),
                                           i32(HD), stream_ptr()), "nv_kv_store_prefill")
+
+
+def kv_store_suffix(qkv, cu, cached, kc, vc, B, T):
+    """Store the K/V column blocks of the packed new rows after the `cached[b]` rows the cache holds for sequence b."""
+    Smax, HD = kc.shape[1], kc.shape[2]
+    check(_lib.load().nv_kv_store_suffix(ptr(qkv), i64(qkv.stride(0)), ptr(cu), ptr(cached), ptr(kc), ptr(vc), i32(B), i32(T),
+                                         i32(Smax), i32(HD), stream_ptr()), "nv_kv_store_suffix")
 
 
 def kv_append(qkv, lens, kc, vc):
