@@ -46,8 +46,8 @@ LEN_LO, LEN_HI = 256, 1024
 
 def gemm_traffic():
     """Average DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-    (profiles/r01_gemm2cta_ncu_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of GEMM launches inside a step)."""
-    p = ROOT / "profiles" / "r01_gemm2cta_ncu_summary.json"
+    (profiles/r01_gemm2cta_v3_ncu_summary.json: dram__bytes_read.sum + dram__bytes_write.sum of GEMM launches inside a step)."""
+    p = ROOT / "profiles" / "r01_gemm2cta_v3_ncu_summary.json"
     if not p.exists():
         return None, None
     unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
