@@ -137,6 +137,15 @@ int nv_gelu_bwd(const float* z, const float* da, float* dz, int64_t n, void* str
 int nv_mha_fwd(const float* qkv, const int* lens, float* out, float* P, int B, int N, int H, int hd, void* stream);
 int nv_mha_bwd(const float* qkv, const float* dout, const float* P, float* dS, float* dqkv, const int* lens, int B, int N,
                int H, int hd, void* stream);
+/* Train-mode dropout of the panorama encoder (nn.Dropout(hidden_dropout_prob), models/image_embedding.py:41,72;
+ * dropout / dropout1 / dropout2 and nn.MultiheadAttention(dropout=...), models/detr_transformer.py:136-146,170-182).
+ * Counter-based RNG: element i is kept iff hash(seed, i) >= p * 2^32, so applying nv_dropout with the same seed to the
+ * upstream gradient is the backward.  nv_mha_*_dropout: Pd [B,H,N,N] = dropped attention probabilities. */
+int nv_dropout(const float* x, float* out, int64_t n, float p_drop, unsigned long long seed, void* stream);
+int nv_mha_fwd_dropout(const float* qkv, const int* lens, float* out, float* P, float* Pd, int B, int N, int H, int hd,
+                       float p_drop, unsigned long long seed, void* stream);
+int nv_mha_bwd_dropout(const float* qkv, const float* dout, const float* P, const float* Pd, float* dS, float* dqkv,
+                       const int* lens, int B, int N, int H, int hd, void* stream);
 int nv_rows_combine(float* out, int64_t ldo, const float* A, int64_t lda, const int* ia, float alpha, const float* Bm,
                     int64_t ldb, const int* ib, float beta, int R, int D, int accumulate, void* stream);
 int nv_rows_scatter_add(float* dst, int64_t ldd, const int* idx, const float* src, int64_t lds, float alpha, int R, int D,

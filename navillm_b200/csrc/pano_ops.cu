@@ -207,15 +207,40 @@ __global__ void gelu_bwd_kernel(const float* __restrict__ z, const float* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
+// Dropout (train mode only; reference: nn.Dropout(hidden_dropout_prob) in models/image_embedding.py:41,72 and
+// dropout / dropout1 / dropout2 + the attention-probability dropout of nn.MultiheadAttention in
+// models/detr_transformer.py:136-146,170-182).  Stateless counter-based RNG: the keep decision of element idx is a
+// hash of (seed, idx), so the backward regenerates the forward's mask from the seed instead of storing it.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rng_u32(uint64_t seed, uint64_t idx) {   // splitmix64 finaliser
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (uint32_t)(z >> 32);
+}
+__device__ __forceinline__ bool rng_keep(uint64_t seed, uint64_t idx, uint32_t thresh) { return rng_u32(seed, idx) >= thresh; }
+
+// out[i] = keep(i) ? x[i] / (1 - p) : 0      (forward on activations, backward on gradients: same seed)
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ out, int64_t n, uint32_t thresh,
+                               float inv_keep, uint64_t seed) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = rng_keep(seed, (uint64_t)i, thresh) ? x[i] * inv_keep : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Small multi-head self-attention with key-padding mask (N <= 256 keys, head_dim <= 128), fp32.
 // qkv: [B, N, 3E] (q | k | v), out: [B, N, E].  One warp per (b, h, query i); probabilities P[b,h,i,:]
 // optionally stored (scratch) for the backward.  Padded query rows (i >= len) produce zeros.
 // ------------------------------------------------------------------------------------------------
 constexpr int MHA_MAXN = 256;
 
+// Attention-probability dropout (Pd != null): Pd = P * keep / (1 - p) is what multiplies V; P (pre-dropout) is
+// still stored for the softmax backward.
 __global__ void __launch_bounds__(128) mha_fwd_kernel(const float* __restrict__ qkv, const int* __restrict__ lens,
                                                       float* __restrict__ out, float* __restrict__ P, int B, int N,
-                                                      int H, int hd, float scale) {
+                                                      int H, int hd, float scale, float* __restrict__ Pd, uint32_t thresh,
+                                                      float inv_keep, uint64_t seed) {
   __shared__ float sc[4][MHA_MAXN];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * 4 + w;
@@ -224,9 +249,11 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const float* __restrict__ 
   const int E = H * hd, len = lens[b];
   float* o = out + ((int64_t)b * N + i) * E + h * hd;
   float* prow = P ? P + (((int64_t)b * H + h) * N + i) * N : nullptr;
+  float* pdrow = Pd ? Pd + (((int64_t)b * H + h) * N + i) * N : nullptr;
   if (i >= len) {
     for (int d = lane; d < hd; d += 32) o[d] = 0.f;
     if (prow) for (int j = lane; j < N; j += 32) prow[j] = 0.f;
+    if (pdrow) for (int j = lane; j < N; j += 32) pdrow[j] = 0.f;
     return;
   }
   const float* q = qkv + ((int64_t)b * N + i) * 3 * E + h * hd;
@@ -251,6 +278,13 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const float* __restrict__ 
   for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
   const float inv = 1.f / sum;
   __syncwarp();
+  if (prow) for (int j = lane; j < N; j += 32) prow[j] = (j < len) ? sc[w][j] * inv : 0.f;
+  if (pdrow) {                                             // dropped probabilities replace sc for the P·V product
+    const uint64_t base = (((uint64_t)b * H + h) * N + i) * (uint64_t)N;
+    for (int j = lane; j < len; j += 32) sc[w][j] = rng_keep(seed, base + j, thresh) ? sc[w][j] * inv_keep : 0.f;
+    __syncwarp();
+    for (int j = lane; j < N; j += 32) pdrow[j] = (j < len) ? sc[w][j] * inv : 0.f;
+  }
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j = 0; j < len; ++j) {
     const float p = sc[w][j] * inv;
@@ -260,15 +294,15 @@ __global__ void __launch_bounds__(128) mha_fwd_kernel(const float* __restrict__ 
   }
 #pragma unroll
   for (int t = 0; t < 4; ++t) if (lane + 32 * t < hd) o[lane + 32 * t] = acc[t];
-  if (prow) for (int j = lane; j < N; j += 32) prow[j] = (j < len) ? sc[w][j] * inv : 0.f;
 }
 
 // Backward pass A: per (b,h,i): dP_ij = dO_i . V_j ; dS_ij = P_ij (dP_ij - sum_j P_ij dP_ij) ; dQ_i = scale sum_j dS_ij K_j.
-// Overwrites nothing of P; writes dS to scratch (same shape as P).
+// Overwrites nothing of P; writes dS to scratch (same shape as P).  With attention dropout Pd = P * m/(1-p) the
+// gradient reaching P is g_ij * m/(1-p) (g = dO_i . V_j), so dS_ij = Pd_ij g_ij - P_ij sum_j Pd_ij g_ij (Pd == P without).
 __global__ void __launch_bounds__(128) mha_bwd_a_kernel(const float* __restrict__ qkv, const float* __restrict__ dout,
                                                         const float* __restrict__ P, float* __restrict__ dS,
                                                         float* __restrict__ dqkv, const int* __restrict__ lens, int B,
-                                                        int N, int H, int hd, float scale) {
+                                                        int N, int H, int hd, float scale, const float* __restrict__ Pd) {
   __shared__ float sd[4][MHA_MAXN];
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t gw = (int64_t)blockIdx.x * 4 + w;
@@ -278,6 +312,7 @@ __global__ void __launch_bounds__(128) mha_bwd_a_kernel(const float* __restrict_
   float* dq = dqkv + ((int64_t)b * N + i) * 3 * E + h * hd;
   float* dsrow = dS + (((int64_t)b * H + h) * N + i) * N;
   const float* prow = P + (((int64_t)b * H + h) * N + i) * N;
+  const float* pdrow = Pd ? Pd + (((int64_t)b * H + h) * N + i) * N : prow;
   if (i >= len) {
     for (int d = lane; d < hd; d += 32) dq[d] = 0.f;
     for (int j = lane; j < N; j += 32) dsrow[j] = 0.f;
@@ -296,12 +331,12 @@ __global__ void __launch_bounds__(128) mha_bwd_a_kernel(const float* __restrict_
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) p += __shfl_xor_sync(0xffffffffu, p, off);
     if (lane == 0) sd[w][j] = p;
-    dot += prow[j] * p;
+    dot += pdrow[j] * p;
   }
   __syncwarp();
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   for (int j = 0; j < len; ++j) {
-    const float ds = prow[j] * (sd[w][j] - dot);
+    const float ds = pdrow[j] * sd[w][j] - prow[j] * dot;
     if (lane == 0) dsrow[j] = ds;
     const float* k = qkv + ((int64_t)b * N + j) * 3 * E + E + h * hd;
 #pragma unroll
@@ -464,7 +499,31 @@ int nv_mha_fwd(const float* qkv, const int* lens, float* out, float* P, int B, i
   NV_REQUIRE(N <= MHA_MAXN && hd <= 128, "nv_mha_fwd: N=%d (max %d) hd=%d (max 128)", N, MHA_MAXN, hd);
   const int64_t warps = (int64_t)B * H * N;
   if (warps == 0) return NV_OK;
-  mha_fwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, lens, out, P, B, N, H, hd, rsqrtf((float)hd));
+  mha_fwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, lens, out, P, B, N, H, hd, rsqrtf((float)hd),
+                                                                      nullptr, 0u, 1.f, 0ull);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+static inline uint32_t drop_thresh(float p) { return (uint32_t)((double)p * 4294967296.0); }
+
+// Train-mode variant with attention-probability dropout: Pd [B,H,N,N] receives the dropped probabilities.
+int nv_mha_fwd_dropout(const float* qkv, const int* lens, float* out, float* P, float* Pd, int B, int N, int H, int hd,
+                       float p_drop, unsigned long long seed, void* stream) {
+  NV_REQUIRE(N <= MHA_MAXN && hd <= 128, "nv_mha_fwd_dropout: N=%d (max %d) hd=%d (max 128)", N, MHA_MAXN, hd);
+  NV_REQUIRE(P && Pd && p_drop >= 0.f && p_drop < 1.f, "nv_mha_fwd_dropout: P, Pd required and 0 <= p < 1");
+  const int64_t warps = (int64_t)B * H * N;
+  if (warps == 0) return NV_OK;
+  mha_fwd_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, lens, out, P, B, N, H, hd, rsqrtf((float)hd), Pd,
+                                                                      drop_thresh(p_drop), 1.f / (1.f - p_drop), seed);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_dropout(const float* x, float* out, int64_t n, float p_drop, unsigned long long seed, void* stream) {
+  if (n == 0) return NV_OK;
+  NV_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "nv_dropout: 0 <= p < 1");
+  dropout_kernel<<<grid_1d(n, 256), 256, 0, S_(stream)>>>(x, out, n, drop_thresh(p_drop), 1.f / (1.f - p_drop), seed);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }
@@ -475,9 +534,23 @@ int nv_mha_bwd(const float* qkv, const float* dout, const float* P, float* dS, f
   const int64_t warps = (int64_t)B * H * N;
   if (warps == 0) return NV_OK;
   const float scale = rsqrtf((float)hd);
-  mha_bwd_a_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, dout, P, dS, dqkv, lens, B, N, H, hd, scale);
+  mha_bwd_a_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, dout, P, dS, dqkv, lens, B, N, H, hd, scale, nullptr);
   NV_LAUNCH_CHECK();
   mha_bwd_b_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, dout, P, dS, dqkv, lens, B, N, H, hd, scale);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+// Backward of nv_mha_fwd_dropout: Pd (dropped probabilities) feeds dV and the dropout part of dS.
+int nv_mha_bwd_dropout(const float* qkv, const float* dout, const float* P, const float* Pd, float* dS, float* dqkv,
+                       const int* lens, int B, int N, int H, int hd, void* stream) {
+  NV_REQUIRE(N <= MHA_MAXN && hd <= 128 && P && Pd, "nv_mha_bwd_dropout: N=%d hd=%d", N, hd);
+  const int64_t warps = (int64_t)B * H * N;
+  if (warps == 0) return NV_OK;
+  const float scale = rsqrtf((float)hd);
+  mha_bwd_a_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, dout, P, dS, dqkv, lens, B, N, H, hd, scale, Pd);
+  NV_LAUNCH_CHECK();
+  mha_bwd_b_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, S_(stream)>>>(qkv, dout, Pd, dS, dqkv, lens, B, N, H, hd, scale);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -8,8 +8,14 @@ in_proj_bias,self_attn.out_proj,linear1,linear2,norm1,norm2}``, ``pano_encoder.n
 checkpoints load.  The torch.nn modules below are parameter holders (and give the reference's default
 initialisation); their ``forward`` is never called -- all arithmetic runs in the C-ABI kernels.
 
-Round-1 scope note: the encoder-internal dropouts (p=0.1, active only in ``train()``) are not applied;
-parity is defined in ``eval()``.  ``fuse_obj`` (off in every reference config) is unsupported.
+Dropout (``train()`` only, like the reference): ``nn.Dropout(hidden_dropout_prob)`` after the embedding LayerNorm
+(models/image_embedding.py:72) and, per encoder layer, the attention-probability dropout of nn.MultiheadAttention plus
+``dropout1`` / ``dropout`` / ``dropout2`` (models/detr_transformer.py:136-146,170-182, p = 0.1).  Masks come from a
+counter-based RNG keyed by (torch.cuda.initial_seed(), call counter, site): the backward regenerates them, the CPU RNG
+stream (which the reference consumes in ``forward_navigation``) is untouched, and a run is reproducible after
+``torch.manual_seed``.  The random STREAM differs from torch's Philox, so train-mode outputs match the reference in
+distribution, not element-wise; element-wise parity is defined in ``eval()``.
+``fuse_obj`` (off in every reference config) is unsupported.
 """
 from __future__ import annotations
 
@@ -36,6 +42,15 @@ class _Encoder(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList([_EncoderLayer(d_model, nhead, dim_ff) for _ in range(num_layers)])
         self.norm = nn.LayerNorm(d_model, eps=1e-12)
+
+
+_DROPOUT_CALLS = [0]
+
+
+def _dropout_seed() -> int:
+    """Base seed of one forward call; site k of the call uses base + k."""
+    _DROPOUT_CALLS[0] += 1
+    return (int(torch.cuda.initial_seed()) * 0x9E3779B1 + _DROPOUT_CALLS[0] * 0x1000003) & (2 ** 63 - 1)
 
 
 def _grad(p: torch.Tensor) -> torch.Tensor:
@@ -85,24 +100,43 @@ class _PanoFn(torch.autograd.Function):
         ops.rows_combine(c, b=mod.nav_type_embedding.weight.data, ib=types32, accumulate=True)
         t["c"] = c
         x, t["m_ln"], t["r_ln"] = _ln_fwd(c, mod.layer_norm)
+        # train-mode dropout: p of the embedding dropout, p_l of the encoder layers (nn.MultiheadAttention(dropout=0.1)
+        # and the three nn.Dropout(0.1) of TransformerEncoderLayer); seeds = base + site index
+        p_emb = float(mod.dropout.p) if mod.training else 0.0
+        p_l = float(mod.encoder_dropout) if mod.training else 0.0
+        seed = _dropout_seed() if (p_emb > 0 or p_l > 0) else 0
+        t["p_emb"], t["p_l"], t["seed"] = p_emb, p_l, seed
+        if p_emb > 0:
+            x = ops.dropout(x, p_emb, seed)
         layers = []
         enc = mod.pano_encoder
         if enc is not None:
-            for lyr in enc.layers:
+            for li, lyr in enumerate(enc.layers):
                 s = {"x": x}
+                sd = seed + 16 * (li + 1)
                 s["h"], s["m1"], s["r1"] = _ln_fwd(x, lyr.norm1)
                 s["qkv"] = ops.sgemm(s["h"], lyr.self_attn.in_proj_weight.data, bias=lyr.self_attn.in_proj_bias.data)
-                att, s["P"] = ops.mha_fwd(s["qkv"].view(B, N, -1), lens32, mod.num_heads)
+                if p_l > 0:
+                    att, s["P"], s["Pd"] = ops.mha_fwd_dropout(s["qkv"].view(B, N, -1), lens32, mod.num_heads, p_l, sd)
+                else:
+                    att, s["P"] = ops.mha_fwd(s["qkv"].view(B, N, -1), lens32, mod.num_heads)
                 s["att"] = att.view(R, -1)
-                x1 = x.clone()
-                _lin_fwd(s["att"], lyr.self_attn.out_proj, out=x1, accumulate=True)
+                if p_l > 0:
+                    x1 = x + ops.dropout(_lin_fwd(s["att"], lyr.self_attn.out_proj), p_l, sd + 1)      # dropout1
+                else:
+                    x1 = x.clone()
+                    _lin_fwd(s["att"], lyr.self_attn.out_proj, out=x1, accumulate=True)
                 s["x1"] = x1
                 s["h2"], s["m2"], s["r2"] = _ln_fwd(x1, lyr.norm2)
                 s["z"] = _lin_fwd(s["h2"], lyr.linear1)
                 s["a1"] = ops.gelu_fwd(s["z"])
-                x2 = x1.clone()
-                _lin_fwd(s["a1"], lyr.linear2, out=x2, accumulate=True)
-                x = x2
+                if p_l > 0:
+                    s["a1"] = ops.dropout(s["a1"], p_l, sd + 2)                                         # dropout (FFN)
+                    x = x1 + ops.dropout(_lin_fwd(s["a1"], lyr.linear2), p_l, sd + 3)                   # dropout2
+                else:
+                    x2 = x1.clone()
+                    _lin_fwd(s["a1"], lyr.linear2, out=x2, accumulate=True)
+                    x = x2
                 layers.append(s)
             t["xe"] = x
             x, t["m_f"], t["r_f"] = _ln_fwd(x, enc.norm)
@@ -127,20 +161,33 @@ class _PanoFn(torch.autograd.Function):
         enc = mod.pano_encoder
         if enc is not None:
             dx = _ln_bwd(dx, t["xe"], enc.norm, t["m_f"], t["r_f"])
-            for lyr, s in zip(reversed(list(enc.layers)), reversed(layers)):
-                da1 = _lin_bwd(dx, s["a1"], lyr.linear2)
+            p_l, seed = t["p_l"], t["seed"]
+            n_l = len(layers)
+            for li, (lyr, s) in enumerate(zip(reversed(list(enc.layers)), reversed(layers))):
+                sd = seed + 16 * (n_l - li)
+                dy2 = ops.dropout(dx, p_l, sd + 3) if p_l > 0 else dx                 # dropout2
+                da1 = _lin_bwd(dy2, s["a1"], lyr.linear2)                             # s["a1"] = dropped activation
+                if p_l > 0:
+                    da1 = ops.dropout(da1, p_l, sd + 2)
                 dz = ops.gelu_bwd(s["z"], da1)
                 dh2 = _lin_bwd(dz, s["h2"], lyr.linear1)
                 dx1 = dx.clone()
                 _ln_bwd(dh2, s["x1"], lyr.norm2, s["m2"], s["r2"], dx=dx1, accumulate_dx=True)
-                datt = _lin_bwd(dx1, s["att"], lyr.self_attn.out_proj)
-                dqkv = ops.mha_bwd(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], ctx.lens32, mod.num_heads).view(R, -1)
+                dy1 = ops.dropout(dx1, p_l, sd + 1) if p_l > 0 else dx1               # dropout1
+                datt = _lin_bwd(dy1, s["att"], lyr.self_attn.out_proj)
+                if p_l > 0:
+                    dqkv = ops.mha_bwd_dropout(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], s["Pd"], ctx.lens32,
+                                               mod.num_heads).view(R, -1)
+                else:
+                    dqkv = ops.mha_bwd(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], ctx.lens32, mod.num_heads).view(R, -1)
                 sa = lyr.self_attn
                 ops.sgemm(dqkv, s["h"], ta=True, tb=True, out=_grad(sa.in_proj_weight), accumulate=True)
                 ops.colsum_(dqkv, _grad(sa.in_proj_bias), accumulate=True)
                 dh = ops.sgemm(dqkv, sa.in_proj_weight.data, tb=True)
                 dx = dx1
                 _ln_bwd(dh, s["x"], lyr.norm1, s["m1"], s["r1"], dx=dx, accumulate_dx=True)
+        if t["p_emb"] > 0:
+            dx = ops.dropout(dx.contiguous(), t["p_emb"], t["seed"])
         dc = _ln_bwd(dx, t["c"], mod.layer_norm, t["m_ln"], t["r_ln"])
         ops.rows_scatter_add_(_grad(mod.nav_type_embedding.weight), ctx.types32, dc)
         dxloc = _ln_bwd(dc, t["xloc"], mod.loc_layer_norm, t["m_loc"], t["r_loc"])
@@ -198,6 +245,7 @@ class ImageEmbeddings(nn.Module):
         self.nav_type_embedding = nn.Embedding(3, H)
         self.layer_norm = nn.LayerNorm(H, eps=1e-12)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
+        self.encoder_dropout = config.hidden_dropout_prob   # models/ops.py:6-12: TransformerEncoderLayer(dropout=hidden_dropout_prob)
         if config.num_pano_layers > 0:
             self.pano_encoder = _Encoder(H, config.num_attention_heads, config.intermediate_size, config.num_pano_layers)
         else:

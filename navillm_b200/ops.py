@@ -5,6 +5,7 @@ launches on the current stream.  Nothing falls back to torch math.
 """
 from __future__ import annotations
 
+import ctypes
 import os
 
 import torch
@@ -394,6 +395,42 @@ def mha_fwd(qkv, lens, n_heads, *, save_probs=True):
     check(_lib.load().nv_mha_fwd(ptr(qkv), ptr(lens), ptr(out), ptr(P), i32(B), i32(N), i32(n_heads), i32(E // n_heads),
                                  stream_ptr()), "nv_mha_fwd")
     return out, P
+
+
+def dropout(x: torch.Tensor, p: float, seed: int, *, out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = keep ? x / (1 - p) : 0 with keep(i) = hash(seed, i) >= p * 2^32 (fp32, contiguous).  Applying it with the same
+    seed to the upstream gradient is the backward."""
+    assert x.dtype == f32_t and x.is_contiguous() and x.is_cuda
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.load().nv_dropout(ptr(x), ptr(out), i64(x.numel()), f32(p), ctypes.c_uint64(seed & (2 ** 64 - 1)), stream_ptr()),
+          "nv_dropout")
+    return out
+
+
+def mha_fwd_dropout(qkv, lens, n_heads, p: float, seed: int):
+    """Train-mode attention with probability dropout: returns (out, P, Pd)."""
+    B, N, E3 = qkv.shape
+    E = E3 // 3
+    assert qkv.is_contiguous() and qkv.dtype == f32_t and lens.dtype == torch.int32
+    out = torch.empty((B, N, E), dtype=f32_t, device=qkv.device)
+    P = torch.empty((B, n_heads, N, N), dtype=f32_t, device=qkv.device)
+    Pd = torch.empty_like(P)
+    check(_lib.load().nv_mha_fwd_dropout(ptr(qkv), ptr(lens), ptr(out), ptr(P), ptr(Pd), i32(B), i32(N), i32(n_heads),
+                                         i32(E // n_heads), f32(p), ctypes.c_uint64(seed & (2 ** 64 - 1)), stream_ptr()),
+          "nv_mha_fwd_dropout")
+    return out, P, Pd
+
+
+def mha_bwd_dropout(qkv, dout, P, Pd, lens, n_heads):
+    B, N, E3 = qkv.shape
+    E = E3 // 3
+    assert dout.is_contiguous() and P.is_contiguous() and Pd.is_contiguous()
+    dqkv = torch.empty_like(qkv)
+    dS = torch.empty_like(P)
+    check(_lib.load().nv_mha_bwd_dropout(ptr(qkv), ptr(dout), ptr(P), ptr(Pd), ptr(dS), ptr(dqkv), ptr(lens), i32(B), i32(N),
+                                         i32(n_heads), i32(E // n_heads), stream_ptr()), "nv_mha_bwd_dropout")
+    return dqkv
 
 
 def mha_bwd(qkv, dout, P, lens, n_heads):

@@ -73,3 +73,97 @@ def test_pano_encoder_matches_oracle(cuda_dev, B, N, lens, with_obj, pano_precis
             continue
         assert p.grad is not None, name
         assert rel_err(p.grad.cpu(), r) < tol_g, f"{name}: {rel_err(p.grad.cpu(), r)}"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# train-mode dropout (models/image_embedding.py:72, models/detr_transformer.py:136-146,170-182)
+# ---------------------------------------------------------------------------------------------------------
+def test_dropout_kernel_statistics_and_determinism(cuda_dev):
+    from navillm_b200 import ops
+    n, p = 1 << 20, 0.1
+    x = torch.randn(n, device=cuda_dev)
+    y = ops.dropout(x, p, seed=1234)
+    keep = y != 0
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5 + 1e-4, frac          # binomial 5 sigma
+    assert torch.allclose(y[keep], x[keep] / (1 - p), rtol=1e-6, atol=0)
+    assert torch.equal(y, ops.dropout(x, p, seed=1234))                               # same seed -> same mask
+    assert not torch.equal(keep, ops.dropout(x, p, seed=1235) != 0)
+    g = ops.dropout(torch.ones_like(x), p, seed=1234)                                 # backward = same op on the gradient
+    assert torch.equal(g != 0, keep)
+    assert torch.equal(ops.dropout(x, 0.0, seed=7), x)
+
+
+def test_mha_dropout_forward_backward_match_torch_with_the_same_mask(cuda_dev):
+    from navillm_b200 import ops
+    B, N, H, hd, p = 3, 36, 4, 32, 0.1
+    E = H * hd
+    g = torch.Generator().manual_seed(5)
+    qkv = torch.randn(B, N, 3 * E, generator=g).to(cuda_dev)
+    lens = torch.tensor([36, 20, 7], dtype=torch.int32, device=cuda_dev)
+    out, P, Pd = ops.mha_fwd_dropout(qkv, lens, H, p, seed=99)
+    valid = (torch.arange(N, device=cuda_dev)[None, :] < lens[:, None])               # [B, N]
+    pair = (valid[:, None, :, None] & valid[:, None, None, :]).expand(B, H, N, N)
+    mask = (Pd != 0)
+    frac = mask[pair].float().mean().item()
+    assert abs(frac - (1 - p)) < 0.02, frac
+    assert torch.allclose(Pd, P * mask / (1 - p), rtol=1e-6, atol=1e-9)
+    # torch reference with the extracted mask
+    x = qkv.clone().requires_grad_(True)
+    q, k, v = [t.view(B, N, H, hd).transpose(1, 2) for t in x.split(E, dim=-1)]
+    s = (q @ k.transpose(-1, -2)) * hd ** -0.5
+    s = s.masked_fill(~valid[:, None, None, :], float("-inf"))
+    pr = torch.softmax(s, dim=-1) * mask / (1 - p)
+    ref = (pr @ v).transpose(1, 2).reshape(B, N, E) * valid[:, :, None]
+    assert torch.allclose(out, ref.detach(), rtol=1e-4, atol=1e-5)
+    go = torch.randn(B, N, E, generator=g).to(cuda_dev) * valid[:, :, None]
+    ref.backward(go)
+    dqkv = ops.mha_bwd_dropout(qkv, go.contiguous(), P, Pd, lens, H)
+    vr = valid[:, :, None].expand(B, N, 3 * E)
+    assert torch.allclose(dqkv[vr], x.grad[vr], rtol=1e-3, atol=1e-4), (dqkv[vr] - x.grad[vr]).abs().max().item()
+
+
+def test_train_mode_dropout_is_applied_and_its_backward_is_consistent(cuda_dev):
+    """Fixed RNG state => the train-mode encoder is a deterministic function; its hand-written backward must agree with
+    central differences along random parameter directions (fp32 GEMMs: 2e-2 relative)."""
+    import navillm_b200.image_embedding as IE
+    from navillm_b200 import ops
+    prev = ops.set_pano_precision("fp32")
+    try:
+        vis_cfg = types.SimpleNamespace(hidden_size=128, num_attention_heads=2, intermediate_size=256, hidden_dropout_prob=0.1,
+                                        image_feat_size=72, angle_feat_size=4, obj_feat_size=40, output_size=256, num_pano_layers=2)
+        torch.manual_seed(0)
+        mod = IE.ImageEmbeddings(vis_cfg, use_obj=False).to(cuda_dev)
+        g = torch.Generator().manual_seed(3)
+        view = torch.randn(2, 12, 72, generator=g).to(cuda_dev)
+        loc = torch.randn(2, 12, 7, generator=g).to(cuda_dev)
+        types_ = torch.randint(0, 2, (2, 12), generator=g).to(cuda_dev)
+        lens = torch.tensor([12, 9], device=cuda_dev)
+        G = torch.randn(2, 12, 256, generator=g).to(cuda_dev)
+
+        def f(train=True):
+            IE._DROPOUT_CALLS[0] = 41                               # same masks on every evaluation
+            mod.train(train)
+            return (mod.forward_panorama_per_step(view, lens, loc, types_)["pano_embeds"] * G).sum()
+
+        with torch.no_grad():
+            assert abs(f(True).item() - f(False).item()) > 1e-3      # dropout changes the output in train()
+            assert f(True).item() == f(True).item()                  # and is reproducible for a fixed call counter
+        mod.zero_grad()
+        f(True).backward()
+        torch.cuda.synchronize()
+        for name in ("img_linear.weight", "pano_encoder.layers.0.linear1.weight", "pano_encoder.layers.1.self_attn.in_proj_weight",
+                     "mapper.weight"):
+            prm = dict(mod.named_parameters())[name]
+            d = torch.randn(prm.shape, generator=g).to(cuda_dev)
+            d = d / d.norm()
+            eps = 2e-2
+            with torch.no_grad():
+                prm.add_(eps * d); fp = f(True).item()
+                prm.sub_(2 * eps * d); fm = f(True).item()
+                prm.add_(eps * d)
+            num = (fp - fm) / (2 * eps)
+            ana = (prm.grad * d).sum().item()
+            assert abs(num - ana) <= 2e-2 * max(abs(num), abs(ana)) + 2e-2, (name, num, ana)
+    finally:
+        ops.set_pano_precision(prev)
