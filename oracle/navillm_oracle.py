@@ -15,8 +15,10 @@ config, AutoConfig, tokenizer): ``tests/golden/make_golden.py`` generates the fi
 (forward outputs, loss and gradients).  The LLaMA block arithmetic is not in the reference tree: it is
 ``transformers.models.llama`` (pinned 4.28.0 by the reference's requirements.txt:20; 5.5.0 is what is
 installed here and what the golden vectors were produced with, attn_implementation="eager").  The
-greedy-decode loop restates HF GenerationMixin greedy search because the reference's
-prepare_inputs_for_generation cannot run under transformers 5.x.
+greedy-decode loop restates HF GenerationMixin greedy search; it is pinned against token ids produced by the
+reference's own generation branch run with a keyword-argument adapter for prepare_inputs_for_generation
+(tests/golden/make_generate_golden.py -> generate_*.pt; the positional call of models/modified_lm.py:187-194 is the
+only thing that does not run under transformers 5.x).
 
 Each function cites the reference file:line it follows (paths relative to /root/reference).
 """

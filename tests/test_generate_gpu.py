@@ -139,3 +139,39 @@ def test_trie_constrained_generation_follows_the_trie_and_the_oracle(cuda_dev):
         assert done or len(node.child) > 0 or True
         gen = [int(x) for x in out[b, S0:] if int(x) not in (eos, tok.unk_token_id)]
         assert any(gen == w[:len(gen)] for w in words), (b, gen)
+
+
+def test_3dqa_generation_matches_reference_generation_branch(cuda_dev):
+    """model('3dqa', training=False) on the kernels against token ids produced by the reference's own generation branch
+    (tests/golden/generate_amp_bf16.pt): identical up to a bf16 near-tie, judged with the oracle's logits."""
+    from oracle import navillm_oracle as O
+    from tests.test_navmodel_gpu import build_model, to_dev
+    from tests.test_oracle_golden import load
+    g, cfg, tok = load("amp_bf16")
+    gen = torch.load(GOLD / "generate_amp_bf16.pt", weights_only=False)
+    model, _ = build_model(g, cuda_dev)
+    n_new, S0 = gen["meta"]["max_new_tokens"], gen["prompt_len"]
+    out = model("3dqa", to_dev(dict(g["qa_in"]), cuda_dev), training=False, max_new_tokens=n_new, do_sample=False)
+    ref_sent = gen["sentences"]
+    assert len(out["generated_sentences"]) == len(ref_sent)
+    # sentence-level equality is the caller-visible contract; allow divergence only after a near-tie step
+    sd = g["state_dict"]
+    qa = g["qa_in"]
+    text = tok(qa["prompts"])
+    feats = qa["features"]
+    lens = torch.tensor([f.shape[0] for f in feats])
+    view = torch.stack([torch.cat([f, f.new_zeros(int(lens.max()) - f.shape[0], f.shape[1])], 0) for f in feats], 0)
+    pano = O.forward_panorama(sd, cfg, view, lens)
+    pe = pano["pano_embeds"] + O._pos_embed(torch.zeros(pano["pano_embeds"].shape[:2] + (14,)), sd, "vp_pos_embeddings")
+    cand = (pe + sd["token_type_embeddings.weight"][0])[pano["pano_masks"]]
+    _, step_logits = O.greedy_generate(sd, cfg, text["input_ids"], text["attention_mask"], cand_vis=cand, max_new_tokens=n_new,
+                                       eos_token_id=tok.eos_token_id, pad_token_id=tok.unk_token_id, return_logits=True)
+    for b, (mine, ref) in enumerate(zip(out["generated_sentences"], ref_sent)):
+        mt, rt = mine.split(), ref.split()
+        for t in range(min(len(mt), len(rt))):
+            if mt[t] == rt[t]:
+                continue
+            top2 = torch.topk(step_logits[t][b], 2).values
+            assert (top2[0] - top2[1]).item() <= 2 * 2.0 ** -8 * top2[0].abs().item(), (b, t, mine, ref)
+            break
+        assert mt[:4] == rt[:4], (mine, ref)

@@ -137,3 +137,42 @@ def test_greedy_generate_is_consistent_with_full_forward():
         cur = torch.cat([cur, nxt[:, None]], 1)
         mask = torch.cat([mask, mask.new_ones(2, 1)], 1)
     assert torch.equal(ids, cur)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "amp_bf16"])
+def test_greedy_generate_matches_reference_generation_branch(precision):
+    """The oracle's restated greedy loop against token ids produced by the reference's own generation branch
+    (models/nav_model.py:386-402 driving HF generate; tests/golden/make_generate_golden.py, which documents the
+    one-line signature adapter needed under transformers 5.x)."""
+    g, cfg, tok = load(precision)
+    gen = torch.load(GOLD / f"generate_{precision}.pt", weights_only=False)
+    sd = g["state_dict"]
+    qa = g["qa_in"]
+    text = tok(qa["prompts"])
+    feats = qa["features"]
+    lens = torch.tensor([f.shape[0] for f in feats])
+    view = torch.stack([torch.cat([f, f.new_zeros(int(lens.max()) - f.shape[0], f.shape[1])], 0) for f in feats], 0)
+    pano = O.forward_panorama(sd, cfg, view, lens)
+    pe = pano["pano_embeds"] + O._pos_embed(torch.zeros(pano["pano_embeds"].shape[:2] + (14,)), sd, "vp_pos_embeddings")
+    pe = pe + sd["token_type_embeddings.weight"][0]
+    cand = pe[pano["pano_masks"]]
+    n_new = gen["meta"]["max_new_tokens"]
+    ids, step_logits = O.greedy_generate(sd, cfg, text["input_ids"], text["attention_mask"], cand_vis=cand, max_new_tokens=n_new,
+                                         eos_token_id=tok.eos_token_id, pad_token_id=tok.unk_token_id, return_logits=True)
+    S0 = gen["prompt_len"]
+    assert S0 == text["input_ids"].shape[1] and torch.equal(ids[:, :S0], gen["ids"][:, :S0])
+    if precision == "fp32":
+        assert torch.equal(ids, gen["ids"]), (ids[:, S0:].tolist(), gen["ids"][:, S0:].tolist())
+        return
+    # bf16: identical until a step whose top-2 logits are within the bf16 noise floor (2 ulp of the top logit); after
+    # such a near-tie the two sequences may legitimately diverge
+    for b in range(ids.shape[0]):
+        for t in range(min(ids.shape[1], gen["ids"].shape[1]) - S0):
+            if ids[b, S0 + t] == gen["ids"][b, S0 + t]:
+                continue
+            top2 = torch.topk(step_logits[t][b], 2).values
+            assert (top2[0] - top2[1]).item() <= 2 * 2.0 ** -8 * top2[0].abs().item(), (b, t, top2.tolist())
+            break
+        else:
+            continue
+    assert torch.equal(ids[:, S0:S0 + 4], gen["ids"][:, S0:S0 + 4])          # the first tokens are far from ties
