@@ -84,47 +84,61 @@ __device__ __forceinline__ void load_tile(uint8_t* dst, const CUtensorMap* m, ui
       tma_load_2d(dst + a * ATOM + r * (64 * 128), m, bar, col + a * 64, row + r * 64);
 }
 
-// Epilogue shared by both passes: accumulator rows -> bf16 (-> inverse RoPE) -> HBM.  The warp owns the 32-column
-// chunks c0 and c0 + 64, i.e. complete rotate-half pairs.
-__device__ __forceinline__ void store_acc_rows(uint32_t tm, uint32_t lane_off, uint32_t c0, bool valid,
-                                               __nv_bfloat16* dst, bool rope, int pos,
-                                               const __nv_bfloat16* __restrict__ cos_t,
-                                               const __nv_bfloat16* __restrict__ sin_t) {
+// Epilogue shared by both passes, in two phases so that HBM sees full 256-byte rows (a row-per-thread store - what the
+// TMEM lane mapping suggests - touches 32 different rows per instruction and, with the per-row cos/sin loads of the fused
+// inverse RoPE, cost 7.5k of a dk/dv CTA's ~28k cycles in the in-kernel trace):
+//   stage_acc_tile   thread = accumulator row: tcgen05.ld its 2 x 32 columns (chunks c0 and c0 + 64), round to bf16,
+//                    write them into a padded row-major smem tile (272-byte rows: conflict-free 16-byte stores);
+//   flush_acc_tile   warp = row: lane l owns columns 4l..4l+3, its rotate-half partner sits in lane l^16; optional
+//                    rotation by -theta[pos] with the rounding points of rope_kernel(sign = -1); 8-byte coalesced stores.
+// The 8 compute warps synchronise on named barrier 1 between the phases; the staging buffers are operand stages that
+// are free once the `done` barrier has fired.
+constexpr uint32_t AB_STAGE_LD = 272;                        // bytes per staged row (256 + 16 padding)
+constexpr uint32_t AB_STAGE_BYTES = 128 * AB_STAGE_LD;       // 34 816 B per accumulator
+
+__device__ __forceinline__ void compute_warps_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void stage_acc_tile(uint32_t tm, uint32_t lane_off, uint32_t c0, uint32_t r, uint8_t* stage) {
   uint32_t a[32], b[32];
   tmem_ld_32x32b_x32(tm + lane_off + c0, a);
   tmem_ld_32x32b_x32(tm + lane_off + c0 + 64, b);
   tmem_ld_wait();
-  if (!valid) return;
-  const __nv_bfloat16* cs = cos_t + (int64_t)pos * 128;
-  const __nv_bfloat16* sn = sin_t + (int64_t)pos * 128;
+  uint8_t* row = stage + r * AB_STAGE_LD;
 #pragma unroll
   for (uint32_t i = 0; i < 32; i += 8) {
     uint4 o1, o2;
-    uint32_t* p1 = &o1.x; uint32_t* p2 = &o2.x;
-    uint4 c1 = make_uint4(0, 0, 0, 0), s1 = c1, c2 = c1, s2 = c1;
-    if (rope) {
-      c1 = *reinterpret_cast<const uint4*>(cs + c0 + i);      s1 = *reinterpret_cast<const uint4*>(sn + c0 + i);
-      c2 = *reinterpret_cast<const uint4*>(cs + 64 + c0 + i); s2 = *reinterpret_cast<const uint4*>(sn + 64 + c0 + i);
+    o1.x = pack_bf16x2(__uint_as_float(a[i]), __uint_as_float(a[i + 1]));     o1.y = pack_bf16x2(__uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
+    o1.z = pack_bf16x2(__uint_as_float(a[i + 4]), __uint_as_float(a[i + 5])); o1.w = pack_bf16x2(__uint_as_float(a[i + 6]), __uint_as_float(a[i + 7]));
+    o2.x = pack_bf16x2(__uint_as_float(b[i]), __uint_as_float(b[i + 1]));     o2.y = pack_bf16x2(__uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
+    o2.z = pack_bf16x2(__uint_as_float(b[i + 4]), __uint_as_float(b[i + 5])); o2.w = pack_bf16x2(__uint_as_float(b[i + 6]), __uint_as_float(b[i + 7]));
+    *reinterpret_cast<uint4*>(row + (c0 + i) * 2) = o1;
+    *reinterpret_cast<uint4*>(row + (c0 + 64 + i) * 2) = o2;
+  }
+}
+
+// cw: compute-warp index 0..7 (rows cw, cw + 8, ...); rows_valid: real rows of the tile; dst: row 0 of the tile at the
+// head's column offset; pos: rotary positions of the tile's rows (null = no rotation).
+__device__ __forceinline__ void flush_acc_tile(const uint8_t* stage, uint32_t cw, uint32_t lane, uint32_t rows_valid,
+                                               __nv_bfloat16* dst, int64_t ld, const int* __restrict__ pos,
+                                               const __nv_bfloat16* __restrict__ cos_t,
+                                               const __nv_bfloat16* __restrict__ sin_t) {
+  const float sgn = lane < 16 ? 1.f : -1.f;
+  for (uint32_t r = cw; r < rows_valid; r += 8) {
+    uint2 x = *reinterpret_cast<const uint2*>(stage + r * AB_STAGE_LD + lane * 8);
+    if (pos != nullptr) {
+      const uint32_t px = __shfl_xor_sync(0xffffffffu, x.x, 16), py = __shfl_xor_sync(0xffffffffu, x.y, 16);
+      const int p = pos[r];
+      const uint2 c = *reinterpret_cast<const uint2*>(cos_t + (int64_t)p * 128 + lane * 4);
+      const uint2 sn = *reinterpret_cast<const uint2*>(sin_t + (int64_t)p * 128 + lane * 4);
+      // y[d] = bf16(x[d] cos) + bf16(x[d+64] sin),  y[d+64] = bf16(x[d+64] cos) + bf16(-x[d] sin)
+      const float y0 = bf16_round(bf16_lo(x.x) * bf16_lo(c.x)) + bf16_round(sgn * bf16_lo(px) * bf16_lo(sn.x));
+      const float y1 = bf16_round(bf16_hi(x.x) * bf16_hi(c.x)) + bf16_round(sgn * bf16_hi(px) * bf16_hi(sn.x));
+      const float y2 = bf16_round(bf16_lo(x.y) * bf16_lo(c.y)) + bf16_round(sgn * bf16_lo(py) * bf16_lo(sn.y));
+      const float y3 = bf16_round(bf16_hi(x.y) * bf16_hi(c.y)) + bf16_round(sgn * bf16_hi(py) * bf16_hi(sn.y));
+      x.x = pack_bf16x2(y0, y1);
+      x.y = pack_bf16x2(y2, y3);
     }
-    const uint32_t* pc1 = &c1.x; const uint32_t* ps1 = &s1.x; const uint32_t* pc2 = &c2.x; const uint32_t* ps2 = &s2.x;
-#pragma unroll
-    for (uint32_t q = 0; q < 4; ++q) {
-      const uint32_t xa = pack_bf16x2(__uint_as_float(a[i + 2 * q]), __uint_as_float(a[i + 2 * q + 1]));
-      const uint32_t xb = pack_bf16x2(__uint_as_float(b[i + 2 * q]), __uint_as_float(b[i + 2 * q + 1]));
-      if (rope) {   // rotation by -theta on the bf16 gradient, same rounding points as rope_kernel(sign = -1)
-        const float y1l = bf16_round(bf16_lo(xa) * bf16_lo(pc1[q])) + bf16_round(bf16_lo(xb) * bf16_lo(ps1[q]));
-        const float y1h = bf16_round(bf16_hi(xa) * bf16_hi(pc1[q])) + bf16_round(bf16_hi(xb) * bf16_hi(ps1[q]));
-        const float y2l = bf16_round(bf16_lo(xb) * bf16_lo(pc2[q])) + bf16_round(-bf16_lo(xa) * bf16_lo(ps2[q]));
-        const float y2h = bf16_round(bf16_hi(xb) * bf16_hi(pc2[q])) + bf16_round(-bf16_hi(xa) * bf16_hi(ps2[q]));
-        p1[q] = pack_bf16x2(y1l, y1h);
-        p2[q] = pack_bf16x2(y2l, y2h);
-      } else {
-        p1[q] = xa;
-        p2[q] = xb;
-      }
-    }
-    *reinterpret_cast<uint4*>(dst + c0 + i) = o1;
-    *reinterpret_cast<uint4*>(dst + c0 + 64 + i) = o2;
+    *reinterpret_cast<uint2*>(dst + (int64_t)r * ld + lane * 4) = x;
   }
 }
 
@@ -322,8 +336,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_wait(done, 0);
     if (warp == 2 && lane == 0) AB_TR(1, 50);
     tc_fence_after();
-    store_acc_rows(tmem_dQ, lane_off, half * 32, row_valid, dq + tok * lddq + head * 128, rope_pos != nullptr,
-                   (rope_pos != nullptr && row_valid) ? rope_pos[tok] : 0, cos_t, sin_t);
+    uint8_t* stage = sKV;                                   // K/V stages are free: every MMA has completed
+    stage_acc_tile(tmem_dQ, lane_off, half * 32, r, stage);
+    compute_warps_sync();
+    const uint32_t rows_valid = min(128u, (uint32_t)seq_len - own * 128);
+    const int64_t tok0 = (int64_t)seq_start + own * 128;
+    flush_acc_tile(stage, warp - 2, lane, rows_valid, dq + tok0 * lddq + head * 128, lddq,
+                   rope_pos != nullptr ? rope_pos + tok0 : nullptr, cos_t, sin_t);
     if (warp == 2 && lane == 0) AB_TR(1, 51);
   }
 
@@ -383,6 +402,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   // 64-query sub-blocks first .. n_qsub-1 can see keys of this block (causal): q >= own*128
   const uint32_t first = 2 * own, n_qsub = (uint32_t)(seq_len + 63) / 64;
   const uint32_t n_it = n_qsub - first;
+  if (threadIdx.x == 0) {
+    AB_TR(0, 0); AB_TRV(0, 3, n_it);
+#ifdef NV_ATTN_TRACE
+    unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); AB_TRV(0, 4, sm);
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); AB_TRV(0, 5, gt);
+#endif
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
@@ -400,6 +426,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 384;
+  if (threadIdx.x == 0) AB_TR(0, 1);
 
   if (warp == 0) {
     const int32_t col = head * 128;
@@ -448,10 +475,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             umma_f16_ss(tmem_base + 128 + b * 64, v_k + ka * (AB_A128 >> 4) + ks * 2, od + ka * (AB_A64 >> 4) + ks * 2,
                         idesc_s, (ka | ks) ? 1u : 0u);
         umma_commit(&sdp_full[b]);
+        if (n < 8) AB_TR(0, 10 + 2 * n);
       }
       __syncwarp();
     };
     mbar_wait(res_full, 0);
+    if (lane == 0) AB_TR(0, 2);
     issue_sdp(0);
     for (uint32_t n = 0; n < n_it; ++n) {
       if (n + 1 < n_it) issue_sdp(n + 1);
@@ -459,6 +488,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       mbar_wait(pds_full, n & 1);
       tc_fence_after();
       if (elect_one()) {
+        if (n < 8) AB_TR(0, 11 + 2 * n);
         // contraction over the 64 queries (4 k-steps); B rows = queries, 64-wide hd atoms AB_A64 apart
         const uint64_t qm = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64), AB_A64, 1024);
         const uint64_t om = qm + (AB_T64 >> 4);
@@ -495,6 +525,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         __syncwarp();
       }
       mbar_wait(&sdp_full[b], (n >> 1) & 1);
+      if (warp == 2 && lane == 0 && n < 8) AB_TR(0, 30 + 2 * n);
       tc_fence_after();
       uint32_t sv[32], dv[32];
       tmem_ld_32x32b_x32(tmem_base + b * 64 + lane_off + half * 32, sv);
@@ -531,19 +562,28 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
+      if (warp == 2 && lane == 0 && n < 8) AB_TR(0, 31 + 2 * n);
     }
     mbar_wait(done, 0);
+    if (warp == 2 && lane == 0) AB_TR(0, 50);
     tc_fence_after();
-    const bool valid = kj < (uint32_t)seq_len;
-    const int64_t tok = (int64_t)seq_start + kj;
-    store_acc_rows(tmem_dV, lane_off, half * 32, valid, dv + tok * lddv + head * 128, false, 0, cos_t, sin_t);
-    store_acc_rows(tmem_dK, lane_off, half * 32, valid, dk + tok * lddk + head * 128, rope_pos != nullptr,
-                   (rope_pos != nullptr && valid) ? rope_pos[tok] : 0, cos_t, sin_t);
+    uint8_t* stage_v = sK;                                  // resident K/V and the Q/dO stages are free now
+    uint8_t* stage_k = sQO;
+    stage_acc_tile(tmem_dV, lane_off, half * 32, r, stage_v);
+    stage_acc_tile(tmem_dK, lane_off, half * 32, r, stage_k);
+    compute_warps_sync();
+    const uint32_t rows_valid = min(128u, (uint32_t)seq_len - own * 128);
+    const int64_t tok0 = (int64_t)seq_start + own * 128;
+    flush_acc_tile(stage_v, cw, lane, rows_valid, dv + tok0 * lddv + head * 128, lddv, nullptr, cos_t, sin_t);
+    flush_acc_tile(stage_k, cw, lane, rows_valid, dk + tok0 * lddk + head * 128, lddk,
+                   rope_pos != nullptr ? rope_pos + tok0 : nullptr, cos_t, sin_t);
+    if (warp == 2 && lane == 0) AB_TR(0, 51);
   }
 
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+  if (threadIdx.x == 32) AB_TR(0, 52);
 }
 
 }  // namespace nv

@@ -279,6 +279,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       mbar_arrive(&p_ready[t]);
     }
     // ---- epilogue ----
+    // Two phases so that HBM sees full 256-byte rows: each thread (= query row) rounds its normalised O row to bf16 into
+    // the group's P tile (free after the last PV; 16-byte chunks XOR-swizzled by the row: conflict-free for the row-per-
+    // thread writes and the row-per-warp reads), then each warp streams whole rows out with 8-byte coalesced stores.
     if (my_blocks > 0) {
       mbar_wait(&pv_done[t], (my_blocks - 1) & 1);
       tc_fence_after();
@@ -286,25 +289,32 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constan
       const bool valid = qi < (uint32_t)seq_len;
       const float inv_l = 1.f / l_run;
       const int64_t tok = (int64_t)seq_start + qi;
-      __nv_bfloat16* orow = O + tok * ldo + head * 128;
+      uint8_t* srow = sPt + r * 256;
 #pragma unroll 1
       for (uint32_t c = 0; c < 128; c += 32) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_O + lane_off + c, v);
         tmem_ld_wait();
-        if (valid) {
 #pragma unroll
-          for (uint32_t i = 0; i < 32; i += 8) {
-            uint4 o;
-            o.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
-            o.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
-            o.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
-            o.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
-            *reinterpret_cast<uint4*>(orow + c + i) = o;
-          }
+        for (uint32_t i = 0; i < 32; i += 8) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[i + 0]) * inv_l, __uint_as_float(v[i + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l);
+          *reinterpret_cast<uint4*>(srow + ((((c + i) >> 3) ^ (r & 15)) << 4)) = o;
         }
       }
       if (valid && lse) lse[(int64_t)head * T + tok] = m_run * scale + __logf(l_run);
+      asm volatile("bar.sync %0, 128;" ::"r"(1 + t) : "memory");        // the tile's four softmax warps
+      const uint32_t rows_valid = min(128u, (uint32_t)seq_len - (q0 + t * 128));
+      const uint32_t wq = warp & 3;
+      __nv_bfloat16* obase = O + ((int64_t)seq_start + q0 + t * 128) * ldo + head * 128;
+      for (uint32_t rr = wq; rr < rows_valid; rr += 4) {
+        const uint32_t chunk = (lane >> 1) ^ (rr & 15);
+        const uint2 x = *reinterpret_cast<const uint2*>(sPt + rr * 256 + (chunk << 4) + ((lane & 1) << 3));
+        *reinterpret_cast<uint2*>(obase + (int64_t)rr * ldo + lane * 4) = x;
+      }
     }
   }
 

@@ -34,10 +34,12 @@ def main():
     L.nv_debug_attn_trace.restype = ctypes.c_int
     L.nv_debug_attn_trace.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
     buf = np.zeros(256 * 64, dtype=np.uint64)
-    n = L.nv_debug_attn_trace(1, buf.ctypes.data, buf.size)
+    kernel = int(sys.argv[1]) if len(sys.argv) > 1 else 1           # 1 = dq pass (default), 0 = dk/dv pass
+    n = L.nv_debug_attn_trace(kernel, buf.ctypes.data, buf.size)
     if n == 0:
         print("library built without -DNV_ATTN_TRACE")
         return
+    print("kernel", "dq" if kernel == 1 else "dkv")
     tr = buf.reshape(256, 64).astype(np.int64)
     nblk = sum((s + 127) // 128 for s in seqlens)
     g0 = min(tr[c, 5] for c in range(nblk) if tr[c, 0])
