@@ -109,18 +109,36 @@ __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_bwd_kernel(
 #pragma unroll
     for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
 
-  for (int row = blockIdx.x; row < T; row += gridDim.x) {
+  // Software pipeline: the x / dy / dres vectors of the NEXT row are requested before the block-wide reduction of the
+  // current row, so loads stay in flight across the two __syncthreads of block_sum (without this the kernel ran at 45 %
+  // of the HBM peak, tools/rowops_bench.py).
+  uint4 xv[RMS_MAX_VEC], gv[RMS_MAX_VEC], rv[RMS_MAX_VEC];
+  auto fetch = [&](int row, uint4 (&xo)[RMS_MAX_VEC], uint4 (&go)[RMS_MAX_VEC], uint4 (&ro)[RMS_MAX_VEC]) {
     const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
     const uint4* dyr = reinterpret_cast<const uint4*>(dy + (int64_t)row * lddy);
+    const uint4* rr = dres ? reinterpret_cast<const uint4*>(dres + (int64_t)row * lddres) : nullptr;
+#pragma unroll
+    for (int i = 0; i < RMS_MAX_VEC; ++i) {
+      const int v = threadIdx.x + i * RMS_THREADS;
+      if (v < nvec) {
+        xo[i] = xr[v];
+        go[i] = dyr[v];
+        if (rr) ro[i] = rr[v];
+      }
+    }
+  };
+  int row = blockIdx.x;
+  if (row < T) fetch(row, xv, gv, rv);
+  for (; row < T; row += gridDim.x) {
+    const int nrow = row + gridDim.x;
+    uint4 nx[RMS_MAX_VEC], ng[RMS_MAX_VEC], nr[RMS_MAX_VEC];
+    if (nrow < T) fetch(nrow, nx, ng, nr);
     const float rs = rstd[row];
-    uint4 xv[RMS_MAX_VEC], gv[RMS_MAX_VEC];
     float dot = 0.f;
 #pragma unroll
     for (int i = 0; i < RMS_MAX_VEC; ++i) {
       const int v = threadIdx.x + i * RMS_THREADS;
       if (v < nvec) {
-        xv[i] = xr[v];
-        gv[i] = dyr[v];
         float xf[8], df[8], wf[8];
         unpack8(xv[i], xf); unpack8(gv[i], df); unpack8(wr[v], wf);
 #pragma unroll
@@ -143,13 +161,15 @@ __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_bwd_kernel(
         for (int j = 0; j < 8; ++j) o[j] = rs * (df[j] * wf[j] - xf[j] * rs * dot);
         if (dres) {
           float rf[8];
-          unpack8(reinterpret_cast<const uint4*>(dres + (int64_t)row * lddres)[v], rf);
+          unpack8(rv[i], rf);
 #pragma unroll
           for (int j = 0; j < 8; ++j) o[j] += rf[j];
         }
         dxr[v] = pack8(o);
       }
     }
+#pragma unroll
+    for (int i = 0; i < RMS_MAX_VEC; ++i) { xv[i] = nx[i]; gv[i] = ng[i]; rv[i] = nr[i]; }
   }
   float* out = dw_partial + (int64_t)blockIdx.x * D;
 #pragma unroll
@@ -517,13 +537,13 @@ int nv_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t l
 }
 
 // workspace: fp32 [nv_rmsnorm_bwd_partials(), D]
-int nv_rmsnorm_bwd_partials(void) { return sm_count() * 4; }
+int nv_rmsnorm_bwd_partials(void) { return sm_count() * 3; }   // 155 registers x 128 threads: three CTAs per SM
 
 int nv_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const float* rstd, const void* dy, int64_t lddy,
                    const void* dres, int64_t lddres, void* dx, int64_t lddx, void* dw, int accumulate_dw,
                    float* workspace, int T, int D, void* stream) {
   NV_REQUIRE(T > 0 && D > 0 && (D & 7) == 0 && D <= 8 * RMS_MAX_VEC * RMS_THREADS, "nv_rmsnorm_bwd: bad T=%d D=%d", T, D);
-  int P = sm_count() * 4;
+  int P = nv_rmsnorm_bwd_partials();
   if (P > T) P = T;
   rmsnorm_bwd_kernel<<<P, RMS_THREADS, 0, S_(stream)>>>(CBF(x), ldx, CBF(w), rstd, CBF(dy), lddy, CBF(dres), lddres,
                                                        BF(dx), lddx, workspace, T, D);
