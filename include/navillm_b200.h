@@ -55,6 +55,9 @@ int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
  * (csrc/gemm_skinny.cu).  C = bf16(bf16(X W^T) + addend), X [M,K], W [N,K] (nn.Linear layout). */
 int nv_gemm_skinny_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, void* C, int64_t ldc, const void* addend,
                         int64_t ld_add, int M, int N, int K, void* stream);
+/* ... with the SwiGLU of HF LlamaMLP fused: h[M,F] = bf16(bf16(silu(g)) * u), [g|u] = bf16(X Wgu^T), Wgu [2F,K] */
+int nv_gemm_skinny_swiglu_bf16(const void* X, int64_t ldx, const void* Wgu, int64_t ldw, void* H, int64_t ldh, int M, int F,
+                               int K, void* stream);
 int nv_gemm_swiglu_bf16(const void* x, int64_t ldx, const void* Wgu, int64_t ldw, void* gu, int64_t ldgu, void* h,
                         int64_t ldh, int M, int F, int K, int keep_gu, void* stream);
 int nv_gemm_dswiglu_bf16(const void* dx, int64_t lddx, const void* Wd, int64_t ldw, const void* gu, int64_t ldgu, void* dgu,
@@ -160,6 +163,9 @@ int nv_kv_store_prefill(const void* qkv, int64_t ld, const int* cu_seqlens, void
                         int Smax, int HD, void* stream);
 int nv_kv_append(const void* qkv, int64_t ld, const int* lens, void* kcache, void* vcache, int B, int Smax, int HD,
                  void* stream);
+/* decode step: rotary embedding of the new token's q,k (in place, position = lens[b]) + append of K (rotated) and V */
+int nv_decode_rope_kv(void* qkv, int64_t ld, const int* lens, const void* cos_t, const void* sin_t, void* kcache, void* vcache,
+                      int B, int Smax, int H, int head_dim, void* stream);
 /* Cross-step prefix-KV reuse in rollouts (caller tasks/agents/mp3d_agent.py:660-726, prompt order
  * tasks/agents/r2r.py:16-31): store the K/V of the NEW rows of each sequence after the cached[b] rows the cache already
  * holds, then attend from the new rows over cached + new keys (nv_attn_fwd_kv). */

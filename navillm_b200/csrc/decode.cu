@@ -50,6 +50,55 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t 
   }
 }
 
+// Decode step: rotary embedding of the new token's q and k heads (in place, rounding points of rope_kernel) fused with
+// the append of its rotated K and its V to the cache at position lens[b] (= the token's rotary position).
+// Work items: [0, B*2H*8) rotate one 8-element chunk pair (d, d + 64) of a q or k head; [.., + B*HD/8) copy one V chunk.
+__global__ void decode_rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const int* __restrict__ lens,
+                                      const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
+                                      __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int Smax, int H) {
+  const int HD = H * 128;
+  const int n_rot = B * 2 * H * 8, n_v = B * (HD >> 3);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_rot + n_v; idx += gridDim.x * blockDim.x) {
+    if (idx < n_rot) {
+      const int c = idx & 7, h = (idx >> 3) % (2 * H), b = idx / (16 * H);
+      const int p = lens[b];
+      __nv_bfloat16* base = qkv + (int64_t)b * ld + h * 128;
+      float x1[8], x2[8], c1[8], s1[8], c2[8], s2[8];
+      unpack8d(*reinterpret_cast<const uint4*>(base + c * 8), x1);
+      unpack8d(*reinterpret_cast<const uint4*>(base + 64 + c * 8), x2);
+      unpack8d(*reinterpret_cast<const uint4*>(cos_t + (int64_t)p * 128 + c * 8), c1);
+      unpack8d(*reinterpret_cast<const uint4*>(sin_t + (int64_t)p * 128 + c * 8), s1);
+      unpack8d(*reinterpret_cast<const uint4*>(cos_t + (int64_t)p * 128 + 64 + c * 8), c2);
+      unpack8d(*reinterpret_cast<const uint4*>(sin_t + (int64_t)p * 128 + 64 + c * 8), s2);
+      uint4 o1, o2;
+      uint32_t* q1 = &o1.x; uint32_t* q2 = &o2.x;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float a0 = bf16_round(x1[j] * c1[j]) + bf16_round(-x2[j] * s1[j]);
+        const float a1 = bf16_round(x1[j + 1] * c1[j + 1]) + bf16_round(-x2[j + 1] * s1[j + 1]);
+        const float b0 = bf16_round(x2[j] * c2[j]) + bf16_round(x1[j] * s2[j]);
+        const float b1 = bf16_round(x2[j + 1] * c2[j + 1]) + bf16_round(x1[j + 1] * s2[j + 1]);
+        q1[j >> 1] = pack_bf16x2(a0, a1);
+        q2[j >> 1] = pack_bf16x2(b0, b1);
+      }
+      *reinterpret_cast<uint4*>(base + c * 8) = o1;
+      *reinterpret_cast<uint4*>(base + 64 + c * 8) = o2;
+      if (h >= H && p < Smax) {                               // a k head: rotated K goes to the cache
+        __nv_bfloat16* dst = kc + ((int64_t)b * Smax + p) * HD + (h - H) * 128;
+        *reinterpret_cast<uint4*>(dst + c * 8) = o1;
+        *reinterpret_cast<uint4*>(dst + 64 + c * 8) = o2;
+      }
+    } else {
+      const int j = idx - n_rot;
+      const int v = j % (HD >> 3), b = j / (HD >> 3);
+      const int p = lens[b];
+      if (p < Smax)
+        *reinterpret_cast<uint4*>(vc + ((int64_t)b * Smax + p) * HD + v * 8) =
+            *reinterpret_cast<const uint4*>(qkv + (int64_t)b * ld + 2 * HD + v * 8);
+    }
+  }
+}
+
 // One new query per sequence over its cache (keys 0..lens[b], the new token included: call after append).
 // CTA = (b, h), 4 warps; half-warps stream keys with 16-byte loads; per-warp online softmax, merged in smem.
 __global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
@@ -265,6 +314,17 @@ int nv_kv_append(const void* qkv, int64_t ld, const int* lens, void* kcache, voi
                  void* stream) {
   if (B == 0) return NV_OK;
   kv_append_kernel<<<(B * (HD >> 3) + 255) / 256, 256, 0, S_(stream)>>>(CBF(qkv), ld, lens, BF(kcache), BF(vcache), B, Smax, HD);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_decode_rope_kv(void* qkv, int64_t ld, const int* lens, const void* cos_t, const void* sin_t, void* kcache, void* vcache,
+                      int B, int Smax, int H, int head_dim, void* stream) {
+  NV_REQUIRE(head_dim == 128 && (ld & 7) == 0, "nv_decode_rope_kv: head_dim must be 128, ld %% 8 == 0");
+  if (B == 0) return NV_OK;
+  const int work = B * 2 * H * 8 + B * (H * 128 / 8);
+  decode_rope_kv_kernel<<<(work + 255) / 256, 256, 0, S_(stream)>>>(BF(qkv), ld, lens, CBF(cos_t), CBF(sin_t), BF(kcache),
+                                                                    BF(vcache), B, Smax, H);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -47,10 +47,13 @@ __device__ __forceinline__ void sk_st_remote_f32(float* p, uint32_t cta, float v
       : "memory");
 }
 
+// swiglu_f != 0: W is the fused gate|up weight [2F, K]; tile n_blk stages 64 gate rows n_blk*64.. and the matching 64 up
+// rows F + n_blk*64.. (two 64-row TMA boxes), the leader pairs them and writes h[m, n] = bf16(bf16(silu(g)) * u), the
+// same rounding points as swiglu_fwd_kernel on the bf16 gate|up buffer (which is not materialised here).
 __global__ void __launch_bounds__(SK_THREADS)
 gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_x,
                     __nv_bfloat16* __restrict__ C, int64_t ldc, const __nv_bfloat16* __restrict__ addend, int64_t ld_add,
-                    uint32_t M, uint32_t N, uint32_t K, uint32_t splits) {
+                    uint32_t M, uint32_t N, uint32_t K, uint32_t splits, uint32_t swiglu_f) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_w = smem;
@@ -84,13 +87,17 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
-    const int32_t n0 = n_blk * SK_BN;
+    const int32_t n0 = swiglu_f ? n_blk * 64 : n_blk * SK_BN;
     for (uint32_t i = 0; i < nkb; ++i) {
       const uint32_t stage = i % SK_STAGES, phase = (i / SK_STAGES) & 1;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[stage], SK_STAGE_BYTES);
         const int32_t k0 = (kb0 + i) * SK_BK;
+        if (swiglu_f) {                                                                 // box {64 k, 64 n}: gate half, up half
+          tma_load_2d(smem_w + stage * SK_W_BYTES, &tmap_w, &full_bar[stage], k0, n0);
+          tma_load_2d(smem_w + stage * SK_W_BYTES + SK_W_BYTES / 2, &tmap_w, &full_bar[stage], k0, (int32_t)swiglu_f + n0);
+        } else
         tma_load_2d(smem_w + stage * SK_W_BYTES, &tmap_w, &full_bar[stage], k0, n0);   // box {64 k, 128 n}
         tma_load_2d(smem_x + stage * SK_X_BYTES, &tmap_x, &full_bar[stage], k0, 0);    // box {64 k, 16 m} (rows >= M: zeros)
       }
@@ -148,7 +155,28 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
           if (m < M) acc[m] += red[(r * SK_BM + m) * SK_BN + nl];
     }
   }
-  if (warp >= 2 && rank == 0) {
+  if (swiglu_f) {
+    // pair lane nl < 64 (gate column) with lane nl + 64 (up column) through the last 8 KB of the weight stages
+    float* ex = red + 7 * SK_BM * SK_BN;
+    if (splits == 1) __syncthreads();                      // (with a cluster the two cluster syncs already ordered the stages)
+    if (warp >= 2 && rank == 0) {
+#pragma unroll
+      for (uint32_t m = 0; m < SK_BM; ++m) ex[m * SK_BN + nl] = bf16_round(acc[m]);
+    }
+    __syncthreads();
+    if (warp >= 2 && rank == 0 && nl < 64) {
+      const uint32_t n = n_blk * 64 + nl;
+      if (n < N) {
+#pragma unroll
+        for (uint32_t m = 0; m < SK_BM; ++m) {
+          if (m < M) {
+            const float g = ex[m * SK_BN + nl], u = ex[m * SK_BN + nl + 64];
+            C[(int64_t)m * ldc + n] = __float2bfloat16_rn(bf16_round(g / (1.f + __expf(-g))) * u);
+          }
+        }
+      }
+    }
+  } else if (warp >= 2 && rank == 0) {
     const uint32_t n = n_blk * SK_BN + nl;
     if (n < N) {
 #pragma unroll
@@ -169,25 +197,20 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
 
 }  // namespace nv
 
-// C[M,N] = bf16( bf16(X[M,K] · W[N,K]^T) (+ addend[M,N]) ), M <= 16.  X, W K-major (nn.Linear weight layout).
-// Same rounding points as nv_gemm_bf16; the fp32 accumulation is split over `splits` k ranges (chosen here).
-extern "C" int nv_gemm_skinny_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, void* C, int64_t ldc,
-                                   const void* addend, int64_t ld_add, int M, int N, int K, void* stream_) {
+static int skinny_launch(const void* X, int64_t ldx, const void* W, int64_t ldw, void* C, int64_t ldc, const void* addend,
+                         int64_t ld_add, int M, int N, int K, uint32_t swiglu_f, cudaStream_t stream) {
   using namespace nv;
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  NV_REQUIRE(M > 0 && M <= (int)SK_BM && N > 0 && K > 0, "nv_gemm_skinny_bf16: needs 1 <= M <= 16 (got M=%d N=%d K=%d)", M, N, K);
-  NV_REQUIRE(X && W && C, "nv_gemm_skinny_bf16: null operand");
-  NV_REQUIRE((ldx & 7) == 0 && (ldw & 7) == 0, "nv_gemm_skinny_bf16: ldx/ldw must be multiples of 8");
   CUtensorMap tw, tx;
   int rc;
-  if ((rc = make_tmap_2d(&tw, W, 2, (uint64_t)K, (uint64_t)N, (uint64_t)ldw * 2, 64, SK_BN))) return rc;
+  const uint64_t w_rows = swiglu_f ? 2ull * swiglu_f : (uint64_t)N;
+  if ((rc = make_tmap_2d(&tw, W, 2, (uint64_t)K, w_rows, (uint64_t)ldw * 2, 64, swiglu_f ? 64 : SK_BN))) return rc;
   if ((rc = make_tmap_2d(&tx, X, 2, (uint64_t)K, (uint64_t)M, (uint64_t)ldx * 2, 64, SK_BM))) return rc;
   static bool attr_set = false;
   if (!attr_set) {
     NV_CUDA(cudaFuncSetAttribute(gemm_skinny_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, SK_DYN_BYTES));
     attr_set = true;
   }
-  const uint32_t tiles = ceil_div_u32(N, SK_BN), total_kb = ceil_div_u32(K, SK_BK);
+  const uint32_t tiles = ceil_div_u32(N, swiglu_f ? 64 : SK_BN), total_kb = ceil_div_u32(K, SK_BK);
   // largest power-of-two split (cluster size <= 8) that keeps about three CTAs per SM and >= 8 k-blocks per CTA
   uint32_t splits = 1;
   while (splits < 8 && tiles * splits * 2 <= 3u * (uint32_t)sm_count() && total_kb / (splits * 2) >= 8) splits *= 2;
@@ -205,6 +228,28 @@ extern "C" int nv_gemm_skinny_bf16(const void* X, int64_t ldx, const void* W, in
   cfg.numAttrs = 1;
   NV_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_tcgen05, tw, tx, reinterpret_cast<__nv_bfloat16*>(C), ldc,
                              reinterpret_cast<const __nv_bfloat16*>(addend), ld_add, (uint32_t)M, (uint32_t)N, (uint32_t)K,
-                             splits));
+                             splits, swiglu_f));
   return NV_OK;
+}
+
+// C[M,N] = bf16( bf16(X[M,K] · W[N,K]^T) (+ addend[M,N]) ), M <= 16.  X, W K-major (nn.Linear weight layout).
+// Same rounding points as nv_gemm_bf16; the fp32 accumulation is split over `splits` k ranges (chosen here).
+extern "C" int nv_gemm_skinny_bf16(const void* X, int64_t ldx, const void* W, int64_t ldw, void* C, int64_t ldc,
+                                   const void* addend, int64_t ld_add, int M, int N, int K, void* stream_) {
+  using namespace nv;
+  NV_REQUIRE(M > 0 && M <= (int)SK_BM && N > 0 && K > 0, "nv_gemm_skinny_bf16: needs 1 <= M <= 16 (got M=%d N=%d K=%d)", M, N, K);
+  NV_REQUIRE(X && W && C, "nv_gemm_skinny_bf16: null operand");
+  NV_REQUIRE((ldx & 7) == 0 && (ldw & 7) == 0, "nv_gemm_skinny_bf16: ldx/ldw must be multiples of 8");
+  return skinny_launch(X, ldx, W, ldw, C, ldc, addend, ld_add, M, N, K, 0u, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+// h[M,F] = bf16( bf16(silu(g)) * u ) with [g | u] = bf16(X[M,K] · Wgu[2F,K]^T): the decode step's gate/up projection and
+// SwiGLU in one kernel (HF LlamaMLP act_fn(gate_proj(x)) * up_proj(x)); F % 64 == 0.
+extern "C" int nv_gemm_skinny_swiglu_bf16(const void* X, int64_t ldx, const void* Wgu, int64_t ldw, void* H, int64_t ldh, int M,
+                                          int F, int K, void* stream_) {
+  using namespace nv;
+  NV_REQUIRE(M > 0 && M <= (int)SK_BM && F > 0 && K > 0 && (F % 64) == 0,
+             "nv_gemm_skinny_swiglu_bf16: needs 1 <= M <= 16 and F %% 64 == 0 (got M=%d F=%d K=%d)", M, F, K);
+  NV_REQUIRE(X && Wgu && H && (ldx & 7) == 0 && (ldw & 7) == 0, "nv_gemm_skinny_swiglu_bf16: null operand / alignment");
+  return skinny_launch(X, ldx, Wgu, ldw, H, ldh, nullptr, 0, M, F, K, (uint32_t)F, reinterpret_cast<cudaStream_t>(stream_));
 }

@@ -391,19 +391,26 @@ class LlamaCore:
         # kernel with 128-column tiles (activations on the UMMA M side) leaves most SMs idle on the 4096-wide
         # projections (32 tiles) and re-stages a mostly-zero 128-row activation tile per k-block.
         bn = DECODE_BLOCK_N
-        if bn == 0 and x.shape[0] <= 16:
+        skinny = bn == 0 and x.shape[0] <= 16
+        fuse_mlp = skinny and d.inter % 64 == 0
+        if skinny:
             lin = lambda a, w, addend=None: ops.gemm_skinny(a, w, addend=addend)
         else:
             lin = lambda a, w, addend=None: ops.gemm(a, w, addend=addend, block_n=bn or 128)
         for l, lyr in enumerate(self.model.layers):
             xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
             qkv = lin(xn, self.wqkv[l])
-            ops.rope_(qkv, lens, self.cos, self.sin, 2 * H, d.head_dim)
-            ops.kv_append(qkv, lens, kc[l], vc[l])
+            if d.head_dim == 128:
+                ops.decode_rope_kv_(qkv, lens, self.cos, self.sin, kc[l], vc[l], H)     # RoPE + cache append in one launch
+            else:
+                ops.rope_(qkv, lens, self.cos, self.sin, 2 * H, d.head_dim)
+                ops.kv_append(qkv, lens, kc[l], vc[l])
             ao = ops.decode_attn(qkv, kc[l], vc[l], lens, H)
             xm = lin(ao, self.wo[l], x)
             xn2, _ = ops.rmsnorm_fwd(xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
-            gu = lin(xn2, self.wgu[l])
-            h = ops.swiglu_fwd(gu)
+            if fuse_mlp:
+                h = ops.gemm_skinny_swiglu(xn2, self.wgu[l])                            # gate|up projection + SwiGLU
+            else:
+                h = ops.swiglu_fwd(lin(xn2, self.wgu[l]))
             x = lin(h, self.wd[l], xm)
         return x

@@ -560,6 +560,28 @@ def gemm_skinny(x: torch.Tensor, w: torch.Tensor, *, addend: torch.Tensor | None
     return out
 
 
+def gemm_skinny_swiglu(x: torch.Tensor, wgu: torch.Tensor, *, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Decode-step gate/up projection + SwiGLU: x [M<=16, K], wgu [2F, K] -> h [M, F] bf16 (gate|up never materialised)."""
+    _rowmajor(x, "x"); _rowmajor(wgu, "wgu")
+    M, K = x.shape
+    F = wgu.shape[0] // 2
+    if wgu.shape[1] != K or M > 16 or F % 64:
+        raise ValueError(f"gemm_skinny_swiglu: x {tuple(x.shape)} wgu {tuple(wgu.shape)} (needs M <= 16, F % 64 == 0)")
+    if out is None:
+        out = torch.empty((M, F), dtype=bf16, device=x.device)
+    check(_lib.load().nv_gemm_skinny_swiglu_bf16(ptr(x), i64(x.stride(0)), ptr(wgu), i64(wgu.stride(0)), ptr(out), i64(out.stride(0)),
+                                                 i32(M), i32(F), i32(K), stream_ptr()), "nv_gemm_skinny_swiglu_bf16")
+    return out
+
+
+def decode_rope_kv_(qkv, lens, cos_t, sin_t, kc, vc, n_heads):
+    """In-place RoPE of the new token's q,k at position lens[b] + append of the rotated K and V to the caches."""
+    B, Smax, HD = kc.shape
+    check(_lib.load().nv_decode_rope_kv(ptr(qkv), i64(qkv.stride(0)), ptr(lens), ptr(cos_t), ptr(sin_t), ptr(kc), ptr(vc), i32(B),
+                                        i32(Smax), i32(n_heads), i32(HD // n_heads), stream_ptr()), "nv_decode_rope_kv")
+    return qkv
+
+
 def gemm_swiglu(x, wgu, *, gu=None, h=None, keep_gu=True):
     """gu = x·Wgu^T ([T,2F]: gate | up) and h = silu(gate)*up ([T,F]) in ONE kernel (SwiGLU epilogue)."""
     _rowmajor(x, "x"); _rowmajor(wgu, "wgu")

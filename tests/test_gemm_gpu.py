@@ -138,3 +138,41 @@ def test_skinny_swap_ab_gemm(cuda_dev, M, N, K, with_add):
     # and against the general kernel: identical up to accumulation order (<= 2 bf16 ulp: accumulator rounding, then the rounded sum with the addend)
     gen = ops.gemm(x, w, addend=add, block_n=128)
     torch.testing.assert_close(out.float(), gen.float(), rtol=1.6e-2, atol=2e-2)
+
+
+@pytest.mark.parametrize("M", [1, 8, 16])
+@pytest.mark.parametrize("F,K", [(11008, 4096), (256, 256), (192, 520)])
+def test_skinny_swiglu_is_bit_identical_to_gemm_then_swiglu(cuda_dev, M, F, K):
+    """Fused gate|up projection + SwiGLU of the decode step vs the two separate kernels (same tiles, same k-splits)."""
+    from navillm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + F + K)
+    x = torch.randn(M, K, generator=g).to(cuda_dev, torch.bfloat16)
+    wgu = (torch.randn(2 * F, K, generator=g) * 0.05).to(cuda_dev, torch.bfloat16)
+    h = ops.gemm_skinny_swiglu(x, wgu)
+    ref = ops.swiglu_fwd(ops.gemm_skinny(x, wgu))
+    torch.cuda.synchronize()
+    assert torch.equal(h, ref)
+    gu = (x.float() @ wgu.float().t()).to(torch.bfloat16).float()
+    want = (torch.nn.functional.silu(gu[:, :F]).to(torch.bfloat16).float() * gu[:, F:]).to(torch.bfloat16).float()
+    torch.testing.assert_close(h.float(), want, rtol=3e-2, atol=3e-2)
+
+
+def test_decode_rope_kv_matches_rope_then_append(cuda_dev):
+    from navillm_b200 import ops
+    from navillm_b200.llama import LlamaDims, rope_tables
+    B, H, Smax = 5, 4, 64
+    HD = H * 128
+    g = torch.Generator(device="cpu").manual_seed(0)
+    qkv = torch.randn(B, 3 * HD, generator=g).to(cuda_dev, torch.bfloat16)
+    lens = torch.tensor([0, 3, 17, 63, 40], dtype=torch.int32, device=cuda_dev)
+    cos, sin = rope_tables(LlamaDims(hidden=H * 128, n_layers=1, n_heads=H, inter=256, vocab=64), cuda_dev)
+    kc = torch.zeros(B, Smax, HD, dtype=torch.bfloat16, device=cuda_dev)
+    vc = torch.zeros_like(kc)
+    a = qkv.clone()
+    ops.decode_rope_kv_(a, lens, cos, sin, kc, vc, H)
+    b = qkv.clone()
+    kc2, vc2 = torch.zeros_like(kc), torch.zeros_like(vc)
+    ops.rope_(b, lens, cos, sin, 2 * H, 128)
+    ops.kv_append(b, lens, kc2, vc2)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(kc, kc2) and torch.equal(vc, vc2)

@@ -51,6 +51,15 @@ def main():
                 i[0] += 1
             ms = timeit(f2)
             print(f"  {name:7s} M=8 N={N} K={K} swap-AB: {ms * 1e3:7.1f} us  {N * K * 2 / ms / 1e6:7.0f} GB/s")
+        if name == "gateup" and hasattr(ops, "gemm_skinny_swiglu"):
+            i = [0]
+            h = torch.empty(8, N // 2, device=dev, dtype=torch.bfloat16)
+
+            def f3():
+                ops.gemm_skinny_swiglu(x, ws[i[0] % 8], out=h)
+                i[0] += 1
+            ms = timeit(f3)
+            print(f"  {name:7s} M=8 N={N} K={K} swap-AB + SwiGLU: {ms * 1e3:7.1f} us  {N * K * 2 / ms / 1e6:7.0f} GB/s")
 
 
 if __name__ == "__main__":
