@@ -511,19 +511,26 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint32_t kj = own * 128 + r;                      // key index inside the sequence
     float* st_l = s_stats[cw][0];
     float* st_d = s_stats[cw][1];
+    // LSE / D of the 32 query columns a warp handles in sub-block n: one coalesced load per lane, shared inside the warp
+    // through smem.  The loads for sub-block n+1 are issued before sub-block n is processed - on the critical path they
+    // cost ~900 cycles of global-load latency per sub-block (in-kernel trace: gap between P^T/dS^T of n and S^T of n+1).
+    auto load_stats = [&](uint32_t n, float& l_out, float& d_out) {
+      const uint32_t qi = (first + n) * 64 + half * 32 + lane;
+      const bool ok = qi < (uint32_t)seq_len;
+      const int64_t tq = (int64_t)seq_start + qi;
+      l_out = ok ? lse[(int64_t)head * T + tq] * LOG2E : INFINITY;   // +inf -> p = 0 for rows past the sequence
+      d_out = ok ? Dvec[(int64_t)head * T + tq] : 0.f;
+    };
+    float cur_l = INFINITY, cur_d = 0.f;
+    if (n_it > 0) load_stats(0, cur_l, cur_d);
     for (uint32_t n = 0; n < n_it; ++n) {
       const uint32_t b = n & 1;
-      // statistics of this warp's 32 query columns: coalesced load, shared inside the warp through smem
       const uint32_t q0 = (first + n) * 64 + half * 32;     // first query of the 32 columns
-      {
-        const uint32_t qi = q0 + lane;
-        const bool ok = qi < (uint32_t)seq_len;
-        const int64_t tq = (int64_t)seq_start + qi;
-        __syncwarp();
-        st_l[lane] = ok ? lse[(int64_t)head * T + tq] * LOG2E : INFINITY;   // +inf -> p = 0 for rows past the sequence
-        st_d[lane] = ok ? Dvec[(int64_t)head * T + tq] : 0.f;
-        __syncwarp();
-      }
+      __syncwarp();
+      st_l[lane] = cur_l;
+      st_d[lane] = cur_d;
+      __syncwarp();
+      if (n + 1 < n_it) load_stats(n + 1, cur_l, cur_d);   // in flight while this sub-block is processed
       mbar_wait(&sdp_full[b], (n >> 1) & 1);
       if (warp == 2 && lane == 0 && n < 8) AB_TR(0, 30 + 2 * n);
       tc_fence_after();
