@@ -127,6 +127,59 @@ class PrefixKVCache:
             self.off[b] = None
 
 
+def plan_prefix_reuse(ids: np.ndarray, msk: np.ndarray, cache: "PrefixKVCache", hist_counts, n_cand_total: int, cand_id: int,
+                      hist_id: int, cls_id: int):
+    """Host-side plan of one cached navigation step (pure numpy; updates ``cache.ids`` / ``cache.off``).
+
+    For every left-padded row: the reusable prefix = longest common token prefix with what the cache holds for the row, cut
+    before the first <cand> token (candidates change every step) and at most L - 1 (the last token is always encoded).
+    Returns per-row lists (new token ids, rotary positions, visual-source indices into cat([cand_vis, hist_vis]),
+    number of new rows, cached rows, total context length) and the packed row index of each row's <cls_1> token."""
+    B, S = ids.shape
+    if B != cache.B:
+        raise ValueError(f"prefix cache was built for batch {cache.B}, got {B} prompts")
+    hist_base = np.concatenate([[0], np.cumsum(np.asarray(hist_counts, dtype=np.int64))])
+    tok_new, pos_new, vis_new, q_lens, cached, kv_len, cls_rows = [], [], [], [], [], [], []
+    n_cand_seen, t0 = 0, 0
+    for b in range(B):
+        toks = ids[b][msk[b]]
+        L = int(toks.size)
+        if L == 0 or not msk[b, S - L:].all():
+            raise ValueError("prefix reuse needs left-padded prompts with at least one token")
+        if L > cache.max_len:
+            raise ValueError(f"prompt of {L} tokens exceeds the prefix cache length {cache.max_len}")
+        if cache.off[b] is None:
+            cache.off[b] = S - L                               # the row keeps this rotary offset for the rollout
+        old = cache.ids[b]
+        m = min(old.size, L - 1)                               # at least the last token is encoded
+        neq = np.flatnonzero(old[:m] != toks[:m])
+        n = int(neq[0]) if neq.size else m
+        cpos = np.flatnonzero(toks == cand_id)                 # candidates change every step: never reused
+        if cpos.size:
+            n = min(n, int(cpos[0]))
+        new = toks[n:]
+        is_h, is_c = new == hist_id, new == cand_id
+        h_before = int((toks[:n] == hist_id).sum())
+        vs = np.full(new.size, -1, dtype=np.int64)
+        vs[is_c] = n_cand_seen + np.arange(int(is_c.sum()))
+        vs[is_h] = n_cand_total + hist_base[b] + h_before + np.arange(int(is_h.sum()))
+        if h_before + int(is_h.sum()) != int(hist_counts[b]):
+            raise RuntimeError(f"row {b}: {h_before + int(is_h.sum())} <hist> tokens but {int(hist_counts[b])} hist_vis rows")
+        n_cand_seen += int(is_c.sum())
+        c = np.flatnonzero(new == cls_id)
+        if c.size != 1:
+            raise RuntimeError(f"expected one <cls_1> token after the reusable prefix of row {b}, found {c.size}")
+        cls_rows.append(t0 + int(c[0]))
+        tok_new.append(new); vis_new.append(vs)
+        pos_new.append(cache.off[b] + n + np.arange(new.size))
+        q_lens.append(int(new.size)); cached.append(n); kv_len.append(L)
+        t0 += int(new.size)
+        cache.ids[b] = toks.copy()
+    if n_cand_seen != n_cand_total:
+        raise RuntimeError(f"{n_cand_seen} <cand> tokens in the prompts but {n_cand_total} cand_vis rows")
+    return tok_new, pos_new, vis_new, q_lens, cached, kv_len, cls_rows
+
+
 class _LMFn(torch.autograd.Function):
     """Differentiable boundary of the language model for a packed prompt.
 
@@ -361,50 +414,11 @@ class ModifiedLlamaForCausalLM(nn.Module):
         dev, d = self._device(), self.dims
         ids = input_ids.detach().cpu().numpy().astype(np.int64)
         msk = attention_mask.detach().cpu().numpy().astype(bool)
-        B, S = ids.shape
-        if B != cache.B:
-            raise ValueError(f"prefix cache was built for batch {cache.B}, got {B} prompts")
-        cand_id, hist_id, cls_id = self.cand_token_id[0], self.hist_token_id[0], self.cls_token_id[0]
-        hist_base = np.concatenate([[0], np.cumsum(np.asarray(hist_counts, dtype=np.int64))])
-        tok_new, pos_new, vis_new, q_lens, cached, kv_len, cls_rows = [], [], [], [], [], [], []
-        n_cand_seen, t0 = 0, 0
+        B = ids.shape[0]
         n_cand_total = 0 if cand_vis is None else cand_vis.shape[0]
-        for b in range(B):
-            toks = ids[b][msk[b]]
-            L = int(toks.size)
-            if L == 0 or not msk[b, S - L:].all():
-                raise ValueError("prefix reuse needs left-padded prompts with at least one token")
-            if L > cache.max_len:
-                raise ValueError(f"prompt of {L} tokens exceeds the prefix cache length {cache.max_len}")
-            if cache.off[b] is None:
-                cache.off[b] = S - L                               # the row keeps this rotary offset for the rollout
-            old = cache.ids[b]
-            m = min(old.size, L - 1)                               # at least the last token is encoded
-            neq = np.flatnonzero(old[:m] != toks[:m])
-            n = int(neq[0]) if neq.size else m
-            cpos = np.flatnonzero(toks == cand_id)                 # candidates change every step: never reused
-            if cpos.size:
-                n = min(n, int(cpos[0]))
-            new = toks[n:]
-            is_h, is_c = new == hist_id, new == cand_id
-            h_before = int((toks[:n] == hist_id).sum())
-            vs = np.full(new.size, -1, dtype=np.int64)
-            vs[is_c] = n_cand_seen + np.arange(int(is_c.sum()))
-            vs[is_h] = n_cand_total + hist_base[b] + h_before + np.arange(int(is_h.sum()))
-            if h_before + int(is_h.sum()) != int(hist_counts[b]):
-                raise RuntimeError(f"row {b}: {h_before + int(is_h.sum())} <hist> tokens but {int(hist_counts[b])} hist_vis rows")
-            n_cand_seen += int(is_c.sum())
-            c = np.flatnonzero(new == cls_id)
-            if c.size != 1:
-                raise RuntimeError(f"expected one <cls_1> token after the reusable prefix of row {b}, found {c.size}")
-            cls_rows.append(t0 + int(c[0]))
-            tok_new.append(new); vis_new.append(vs)
-            pos_new.append(cache.off[b] + n + np.arange(new.size))
-            q_lens.append(int(new.size)); cached.append(n); kv_len.append(L)
-            t0 += int(new.size)
-            cache.ids[b] = toks.copy()
-        if n_cand_seen != n_cand_total:
-            raise RuntimeError(f"{n_cand_seen} <cand> tokens in the prompts but {n_cand_total} cand_vis rows")
+        plan = plan_prefix_reuse(ids, msk, cache, hist_counts, n_cand_total, self.cand_token_id[0], self.hist_token_id[0],
+                                 self.cls_token_id[0])
+        tok_new, pos_new, vis_new, q_lens, cached, kv_len, cls_rows = plan
         cu = np.concatenate([[0], np.cumsum(q_lens)])
         kv_start = np.arange(B, dtype=np.int64) * cache.max_len
         parts = [np.concatenate(tok_new), np.concatenate(pos_new), cu, np.concatenate(vis_new), np.asarray(cls_rows),

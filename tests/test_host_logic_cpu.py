@@ -64,3 +64,80 @@ def test_oracle_rope_tables_match_product_tables():
     cfg = O.OracleConfig(hidden=256, n_heads=2)
     c2, s2 = O.rope_tables(cfg, torch.arange(64)[None], torch.bfloat16)
     assert torch.equal(cos, c2[0]) and torch.equal(sin, s2[0])
+
+
+# ---------------------------------------------------------------------------------------------------------
+# cross-step prefix-KV reuse: host-side planning (navillm_b200.modified_lm.plan_prefix_reuse)
+# ---------------------------------------------------------------------------------------------------------
+def _left_pad(rows, pad=0):
+    import numpy as np
+    S = max(len(r) for r in rows)
+    ids = np.full((len(rows), S), pad, dtype=np.int64)
+    msk = np.zeros((len(rows), S), dtype=bool)
+    for i, r in enumerate(rows):
+        ids[i, S - len(r):] = r
+        msk[i, S - len(r):] = True
+    return ids, msk
+
+
+def test_prefix_reuse_plan_over_a_three_step_rollout():
+    import types
+    import numpy as np
+    import pytest
+    from navillm_b200.modified_lm import plan_prefix_reuse
+    CAND, HIST, CLS = 900, 901, 902
+    cache = types.SimpleNamespace(B=2, max_len=64, ids=[np.zeros(0, dtype=np.int64) for _ in range(2)], off=[None, None])
+    instr = [[1, 5, 6, 7, 8], [1, 9, 10]]
+
+    def prompt(b, t, n_cand):
+        p = list(instr[b]) + [20]
+        for i in range(t):
+            p += [30 + i, HIST]
+        p += [21] + [x for j in range(n_cand) for x in (40 + j, CAND)] + [22, CLS]
+        return p
+
+    # step 0: nothing cached, everything is encoded; positions = left-pad offset + index (HF arange over the padded row)
+    rows = [prompt(0, 0, 2), prompt(1, 0, 3)]
+    ids, msk = _left_pad(rows)
+    tok, pos, vis, ql, cached, kvl, cls = plan_prefix_reuse(ids, msk, cache, [0, 0], 5, CAND, HIST, CLS)
+    S0 = ids.shape[1]
+    assert cached == [0, 0] and ql == [len(rows[0]), len(rows[1])] and kvl == ql
+    assert cache.off == [S0 - len(rows[0]), S0 - len(rows[1])]
+    assert pos[0].tolist() == list(range(cache.off[0], cache.off[0] + len(rows[0])))
+    assert [int(v) for v in vis[0] if v >= 0] == [0, 1] and [int(v) for v in vis[1] if v >= 0] == [2, 3, 4]     # row-major <cand> order
+    assert cls == [len(rows[0]) - 1, len(rows[0]) + len(rows[1]) - 1]
+    off = list(cache.off)
+
+    # step 1: one <hist> per row; the prefix up to the end of the old history section is reused
+    rows = [prompt(0, 1, 3), prompt(1, 1, 1)]
+    ids, msk = _left_pad(rows)
+    tok, pos, vis, ql, cached, kvl, cls = plan_prefix_reuse(ids, msk, cache, [1, 1], 4, CAND, HIST, CLS)
+    assert cached == [len(instr[0]) + 1, len(instr[1]) + 1]                   # instruction + the "history" marker token 20
+    assert cache.off == off                                                   # rows keep their first-step rotary offset
+    assert pos[0][0] == off[0] + cached[0] and kvl == [len(rows[0]), len(rows[1])]
+    # visual sources: candidates first (row-major over the batch), then hist rows flattened sample-major
+    assert [int(v) for v in vis[0] if v >= 0] == [4 + 0, 0, 1, 2] and [int(v) for v in vis[1] if v >= 0] == [4 + 1, 3]
+
+    # step 2: the first <hist> is now part of the reusable prefix; the second one is new
+    rows = [prompt(0, 2, 1), prompt(1, 2, 1)]
+    ids, msk = _left_pad(rows)
+    tok, pos, vis, ql, cached, kvl, cls = plan_prefix_reuse(ids, msk, cache, [2, 2], 2, CAND, HIST, CLS)
+    assert cached == [len(instr[0]) + 1 + 2, len(instr[1]) + 1 + 2]
+    assert [int(v) for v in vis[0] if v >= 0] == [2 + 0 + 1, 0] and [int(v) for v in vis[1] if v >= 0] == [2 + 2 + 1, 1]
+    assert tok[0][0] == 31 and tok[0][-1] == CLS
+
+    # a different instruction in row 1 (new episode without reset): nothing of that row is reused
+    instr[1] = [1, 11, 12]
+    rows = [prompt(0, 2, 1), prompt(1, 2, 1)]
+    ids, msk = _left_pad(rows)
+    _, _, _, _, cached, _, _ = plan_prefix_reuse(ids, msk, cache, [2, 2], 2, CAND, HIST, CLS)
+    assert cached[0] == rows[0].index(CAND) and cached[1] == 1                # row 0: everything before its first <cand>
+
+    # contract violations fail loudly
+    with pytest.raises(RuntimeError, match="hist_vis rows"):
+        plan_prefix_reuse(ids, msk, cache, [2, 1], 2, CAND, HIST, CLS)
+    with pytest.raises(RuntimeError, match="cand_vis rows"):
+        plan_prefix_reuse(ids, msk, cache, [2, 2], 3, CAND, HIST, CLS)
+    cache.max_len = 8
+    with pytest.raises(ValueError, match="exceeds the prefix cache length"):
+        plan_prefix_reuse(ids, msk, cache, [2, 2], 2, CAND, HIST, CLS)
