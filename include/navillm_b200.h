@@ -49,7 +49,9 @@ int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B, int64_t ld
 /* Fused-epilogue forms on the CTA-pair kernel (csrc/gemm_bf16_2cta.cu), bit-identical to the unfused sequences:
  *   nv_gemm_swiglu_bf16   gu = x Wgu^T and h = silu(gate)*up        (HF LlamaMLP: act_fn(gate_proj(x)) * up_proj(x))
  *   nv_gemm_dswiglu_bf16  dgu = swiglu'(gu) o (dx Wd)               (autograd of the above through down_proj)
- *   nv_gemm_rope_bf16     qkv = x Wqkv^T with rotate-half RoPE on the q,k columns (HF apply_rotary_pos_emb) */
+ *   nv_gemm_rope_bf16     qkv = x Wqkv^T with rotate-half RoPE on the q,k columns (HF apply_rotary_pos_emb)
+ *   nv_gemm_attnd_bf16    dO = dY Wo (o_proj dgrad) and D[h,t] = sum_d dO O of the attention backward (same values as
+ *                         the separate row-sum kernel up to fp32 summation order) */
 /* Decode-step GEMM (M <= 16 rows, reference: HF generate through models/modified_lm.py:184-199): swap-AB tcgen05
  * kernel with the K range split over a thread-block cluster and reduced through distributed shared memory
  * (csrc/gemm_skinny.cu).  C = bf16(bf16(X W^T) + addend), X [M,K], W [N,K] (nn.Linear layout). */
@@ -62,6 +64,8 @@ int nv_gemm_swiglu_bf16(const void* x, int64_t ldx, const void* Wgu, int64_t ldw
                         int64_t ldh, int M, int F, int K, int keep_gu, void* stream);
 int nv_gemm_dswiglu_bf16(const void* dx, int64_t lddx, const void* Wd, int64_t ldw, const void* gu, int64_t ldgu, void* dgu,
                          int64_t lddgu, int M, int F, int D, void* stream);
+int nv_gemm_attnd_bf16(const void* dy, int64_t lddy, const void* Wo, int64_t ldw, const void* o, int64_t ldo, void* dout,
+                       int64_t lddo, float* dvec, int M, int D, int Dout, void* stream);
 int nv_gemm_rope_bf16(const void* x, int64_t ldx, const void* W, int64_t ldw, void* out, int64_t ldo, const int* pos,
                       const void* cos_t, const void* sin_t, int M, int N, int K, int rope_cols, void* stream);
 

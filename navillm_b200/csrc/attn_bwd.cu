@@ -610,7 +610,8 @@ extern "C" int nv_debug_attn_trace(int kernel, unsigned long long* out, int max_
 }
 
 // Inputs: q,k,v (post-RoPE) and o, do as bf16 [T, H*128]-column views; lse [H,T] from the forward.
-// dvec: fp32 workspace [H, T].  Outputs dq, dk, dv: bf16 views with their own leading dimensions.
+// dvec: fp32 workspace [H, T] (computed here from o and dout; with o == nullptr it must already hold
+// D[h,t] = sum_d dout[t,h,d] o[t,h,d]).  Outputs dq, dk, dv: bf16 views with their own leading dimensions.
 // rope_pos/cos_t/sin_t (nullable): when given, dq and dk are rotated back by -theta[pos] in the epilogue, i.e. the
 // outputs are the gradients w.r.t. the PRE-RoPE q/k (fuses the backward of the rotary embedding).
 extern "C" int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
@@ -636,7 +637,7 @@ extern "C" int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
     NV_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DkvSmem::DYN_BYTES));
     attr_set = true;
   }
-  {
+  if (o != nullptr) {     // o == nullptr: dvec already holds D (written by the o_proj dgrad epilogue, nv_gemm_attnd_bf16)
     const int64_t threads = (int64_t)T * H * 32;
     attn_bwd_prep_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(o), ldo, reinterpret_cast<const __nv_bfloat16*>(dout), lddo, dvec, T, H);

@@ -176,14 +176,17 @@ __device__ __forceinline__ void tile_coords2(uint32_t tile, uint32_t num_m, uint
 //               for the backward) and h = bf16(bf16(silu(g)) * u) into aux [T,F]   (HF LlamaMLP act_fn(gate)*up)
 //   EPI_DSWIGLU down-projection dgrad: acc = dh; reads g,u from aux [T,2F] and writes dg = dh*u*silu'(g),
 //               du = dh*silu(g) into C [T,2F] (the separate swiglu_bwd pass and the dh round trip disappear)
+//   EPI_ATTND   o_proj dgrad: C = dO (gradient of the attention output) and, per row and 128-column head, the
+//               D[h, t] = sum_d dO[t,h,d] * O[t,h,d] vector of the attention backward (aux = O; replaces attn_bwd_prep)
 //   EPI_ROPE    fused q|k|v projection: columns < rope_cols get the rotate-half rotary embedding
 //               (HF apply_rotary_pos_emb, bf16 rounding points preserved) with cos/sin[pos[row]] before the store
-enum { EPI_PLAIN = 0, EPI_SWIGLU = 1, EPI_DSWIGLU = 2, EPI_ROPE = 3 };
+enum { EPI_PLAIN = 0, EPI_SWIGLU = 1, EPI_DSWIGLU = 2, EPI_ROPE = 3, EPI_ATTND = 4 };
 
 struct EpiAux {
   void* aux;            // SWIGLU: h out [T,F];  DSWIGLU: gu in [T,2F]
   int64_t ld_aux;
   uint32_t F;           // SWIGLU / DSWIGLU: intermediate size (columns of gate and of up)
+  float* dvec;          // ATTND: D out [H, T] fp32 (T = M rows)
   const int* pos;       // ROPE
   const __nv_bfloat16* cos_t;
   const __nv_bfloat16* sin_t;
@@ -457,6 +460,36 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             }
           }
         }
+      } else if constexpr (EPI == EPI_ATTND) {
+        // N % 128 == 0 and 16-byte aligned rows are required by the host wrapper
+        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(Cout) + static_cast<int64_t>(row) * ldc;
+        const __nv_bfloat16* orow = reinterpret_cast<const __nv_bfloat16*>(ea.aux) + static_cast<int64_t>(row) * ea.ld_aux;
+        float dsum = 0.f;
+#pragma unroll 1
+        for (uint32_t c = 0; c < G2_BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c, v);
+          tmem_ld_wait();
+          const uint32_t col = col0 + c;
+          if (row < M && col < N) {
+#pragma unroll
+            for (uint32_t j = 0; j < 32; j += 8) {
+              uint4 o;
+              o.x = pack_bf16x2(__uint_as_float(v[j + 0]), __uint_as_float(v[j + 1]));
+              o.y = pack_bf16x2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              o.z = pack_bf16x2(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5]));
+              o.w = pack_bf16x2(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7]));
+              const uint4 a = *reinterpret_cast<const uint4*>(orow + col + j);
+              dsum += bf16_lo(o.x) * bf16_lo(a.x) + bf16_hi(o.x) * bf16_hi(a.x) + bf16_lo(o.y) * bf16_lo(a.y) + bf16_hi(o.y) * bf16_hi(a.y)
+                    + bf16_lo(o.z) * bf16_lo(a.z) + bf16_hi(o.z) * bf16_hi(a.z) + bf16_lo(o.w) * bf16_lo(a.w) + bf16_hi(o.w) * bf16_hi(a.w);
+              *reinterpret_cast<uint4*>(drow + col + j) = o;
+            }
+            if ((c & 127u) == 96u) {                       // a 128-column head is complete
+              ea.dvec[static_cast<int64_t>(col >> 7) * M + row] = dsum;
+              dsum = 0.f;
+            }
+          }
+        }
       } else {
 #pragma unroll 1
       for (uint32_t c = 0; c < G2_BN; c += 32) {
@@ -635,6 +668,23 @@ int nv_gemm_dswiglu_bf16(const void* dx, int64_t lddx, const void* Wd, int64_t l
   ea.aux = const_cast<void*>(gu); ea.ld_aux = ldgu; ea.F = (uint32_t)F;
   return launch_gemm_2cta<false, true, EPI_DSWIGLU>(ta, tb, dgu, lddgu, nullptr, 0, M, F, D, 0u,
                                                     reinterpret_cast<cudaStream_t>(stream), ea);
+}
+
+// dO[T, D] = dY[T, Dout] · Wo[Dout, D]  (o_proj dgrad; Wo is the nn.Linear weight, B stored [K = Dout, N = D]) and, in the
+// same epilogue, dvec[h, t] = sum_d bf16(dO[t, h*128+d]) * O[t, h*128+d]: the D vector of the attention backward.
+int nv_gemm_attnd_bf16(const void* dy, int64_t lddy, const void* Wo, int64_t ldw, const void* o, int64_t ldo, void* dout,
+                       int64_t lddo, float* dvec, int M, int D, int Dout, void* stream) {
+  using namespace nv;
+  NV_REQUIRE(M > 0 && D > 0 && Dout > 0 && (D % 128) == 0 && o && dvec, "nv_gemm_attnd_bf16: D %% 128 and O / dvec required");
+  NV_REQUIRE((lddy & 7) == 0 && (ldw & 7) == 0 && (ldo & 7) == 0 && (lddo & 7) == 0, "nv_gemm_attnd_bf16: alignment");
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, dy, 2, (uint64_t)Dout, (uint64_t)M, (uint64_t)lddy * 2, 64, G2_BM))) return rc;
+  if ((rc = make_tmap_2d(&tb, Wo, 2, (uint64_t)D, (uint64_t)Dout, (uint64_t)ldw * 2, 64, G2_BK))) return rc;
+  EpiAux ea{};
+  ea.aux = const_cast<void*>(o); ea.ld_aux = ldo; ea.dvec = dvec;
+  return launch_gemm_2cta<false, true, EPI_ATTND>(ta, tb, dout, lddo, nullptr, 0, M, D, Dout, 0u,
+                                                  reinterpret_cast<cudaStream_t>(stream), ea);
 }
 
 // qkv[T, N] = x[T,K] · Wqkv[N,K]^T with rotate-half RoPE applied to the first rope_cols columns (q and k heads).

@@ -351,7 +351,11 @@ class LlamaCore:
                                   dw=lyr.post_attention_layernorm.weight.grad, accumulate_dw=acc)
             del dxn2
             # ---- attention:  xm = x + o_proj(attn(rope(qkv(rmsnorm1(x))))) ----
-            dao = ops.gemm(dxm, self.wo[l], b_mn=True)
+            dvec = None
+            if s.rows is None and self.fused_epilogues and dxm.shape[0] >= 1024 and d.head_dim == 128:
+                dao, dvec = ops.gemm_attnd(dxm, self.wo[l], s.ao)      # dgrad + the attention backward's D in the epilogue
+            else:
+                dao = ops.gemm(dxm, self.wo[l], b_mn=True)
             if s.rows is None:
                 ops.gemm(dxm, s.ao, a_mn=True, b_mn=True, out=self.go[l], addend=add(self.go[l]))
             else:
@@ -364,7 +368,7 @@ class LlamaCore:
                 ops.scatter_rows_(dxm, s.rows, full)
                 dxm = full
             # attention backward with the inverse rotary embedding of dq/dk fused into its epilogue
-            dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H, rope=(pos, self.cos, self.sin))
+            dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H, rope=(pos, self.cos, self.sin), dvec=dvec)
             del dao
             dxn = ops.gemm(dqkv, self.wqkv[l], b_mn=True)
             ops.gemm(dqkv, s.xn, a_mn=True, b_mn=True, out=self.gqkv[l], addend=add(self.gqkv[l]))

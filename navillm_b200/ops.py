@@ -271,9 +271,11 @@ def ce_fwd_bwd(logits, labels, special_ids, *, grad_scale=None):
 
 
 def attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Tensor, cu_seqlens: torch.Tensor, seqlens,
-             n_heads: int, *, dqkv: torch.Tensor | None = None, scale: float | None = None, rope=None) -> torch.Tensor:
+             n_heads: int, *, dqkv: torch.Tensor | None = None, scale: float | None = None, rope=None,
+             dvec: torch.Tensor | None = None) -> torch.Tensor:
     """Backward of attn_fwd (csrc/attn_bwd.cu): returns dqkv [T, 3*H*128] bf16 (dq | dk | dv).
-    rope = (pos int32 [T], cos_t, sin_t): also undo the rotary embedding in the epilogue (gradients w.r.t. pre-RoPE q/k)."""
+    rope = (pos int32 [T], cos_t, sin_t): also undo the rotary embedding in the epilogue (gradients w.r.t. pre-RoPE q/k).
+    dvec: fp32 [H*T] already holding D[h,t] = sum_d do·o (from gemm_attnd) -> the row-sum kernel is skipped."""
     T, W = qkv.shape
     hd = 128
     HD = n_heads * hd
@@ -281,17 +283,21 @@ def attn_bwd(qkv: torch.Tensor, o: torch.Tensor, do: torch.Tensor, lse: torch.Te
         dqkv = torch.empty((T, W), dtype=bf16, device=qkv.device)
     if scale is None:
         scale = hd ** -0.5
-    dvec = _workspace(qkv.device, n_heads * T + 16)
+    have_d = dvec is not None
+    if not have_d:
+        dvec = _workspace(qkv.device, n_heads * T + 16)
     q, k, v = qkv[:, :HD], qkv[:, HD:2 * HD], qkv[:, 2 * HD:]
     dq, dk, dv = dqkv[:, :HD], dqkv[:, HD:2 * HD], dqkv[:, 2 * HD:]
     ld = qkv.stride(0)
-    check(_lib.load().nv_attn_bwd(ptr(q), i64(ld), ptr(k), i64(ld), ptr(v), i64(ld), ptr(o), i64(o.stride(0)), ptr(do),
+    check(_lib.load().nv_attn_bwd(ptr(q), i64(ld), ptr(k), i64(ld), ptr(v), i64(ld), ptr(None if have_d else o), i64(o.stride(0)), ptr(do),
                                   i64(do.stride(0)), ptr(lse), ptr(dvec), ptr(dq), i64(dqkv.stride(0)), ptr(dk),
                                   i64(dqkv.stride(0)), ptr(dv), i64(dqkv.stride(0)), ptr(cu_seqlens), i32(len(seqlens)),
                                   i32(T), i32(n_heads), i32(hd), i32(_qblocks(seqlens)), f32(scale),
                                   ptr(rope[0] if rope else None), ptr(rope[1] if rope else None), ptr(rope[2] if rope else None),
                                   stream_ptr()),
           "nv_attn_bwd")
+    if have_d:
+        _lib.launch_count -= 1          # the row-sum kernel was not launched
     return dqkv
 
 
@@ -612,6 +618,25 @@ def gemm_dswiglu(dx, wd, gu, *, dgu=None):
                          "nv_gemm_dswiglu_bf16"),
            2.0 * T * F * D, 2.0 * (T * D + F * D + 4 * T * F))
     return dgu
+
+
+def gemm_attnd(dy, wo, o, *, dout=None, dvec=None):
+    """o_proj dgrad dO = dy·Wo ([T,D]) with the attention backward's D[h,t] = sum_d dO·O computed in the epilogue.
+    Returns (dO bf16 [T,D], dvec fp32 [H*T]); pass dvec to attn_bwd(..., dvec=dvec) to skip its row-sum kernel."""
+    _rowmajor(dy, "dy"); _rowmajor(wo, "wo"); _rowmajor(o, "o")
+    T, Dout = dy.shape
+    D = wo.shape[1]
+    assert wo.shape[0] == Dout and o.shape == (T, D) and D % 128 == 0
+    if dout is None:
+        dout = torch.empty((T, D), dtype=bf16, device=dy.device)
+    if dvec is None:
+        dvec = torch.empty(((D // 128) * T,), dtype=torch.float32, device=dy.device)
+    lib = _lib.load()
+    _timed(lambda: check(lib.nv_gemm_attnd_bf16(ptr(dy), i64(dy.stride(0)), ptr(wo), i64(wo.stride(0)), ptr(o), i64(o.stride(0)),
+                                                 ptr(dout), i64(dout.stride(0)), ptr(dvec), i32(T), i32(D), i32(Dout), stream_ptr()),
+                         "nv_gemm_attnd_bf16"),
+           2.0 * T * D * Dout, 2.0 * (T * Dout + D * Dout + 2 * T * D))
+    return dout, dvec
 
 
 def gemm_rope(x, w, pos, cos_t, sin_t, rope_cols, *, out=None):

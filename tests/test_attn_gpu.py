@@ -85,3 +85,32 @@ def test_attn_bwd_fused_inverse_rope_is_bit_identical(cuda_dev):
     ops.rope_(plain, pos, cos_t, sin_t, 2 * H, backward=True)
     torch.cuda.synchronize()
     assert torch.equal(fused, plain)
+
+
+def test_o_proj_dgrad_with_fused_attention_D(cuda_dev):
+    """nv_gemm_attnd_bf16: dO is bit-identical to the plain dgrad GEMM; D matches the fp32 row sums of dO * O; the
+    attention backward fed with it agrees with the one that runs its own row-sum kernel."""
+    import numpy as np
+    from navillm_b200 import ops
+    H, HD = 8, 128
+    D = H * HD
+    seqlens = [700, 324, 1024]
+    T = sum(seqlens)
+    g = torch.Generator().manual_seed(4)
+    dy = torch.randn(T, D, generator=g).to(cuda_dev, torch.bfloat16)
+    wo = (torch.randn(D, D, generator=g) * 0.03).to(cuda_dev, torch.bfloat16)
+    qkv = torch.randn(T, 3 * D, generator=g).to(cuda_dev, torch.bfloat16)
+    cu = torch.tensor([0] + list(np.cumsum(seqlens)), dtype=torch.int32, device=cuda_dev)
+    o, lse = ops.attn_fwd(qkv, cu, seqlens, H)
+    dout, dvec = ops.gemm_attnd(dy, wo, o)
+    ref = ops.gemm(dy, wo, b_mn=True, block_n=512)
+    torch.cuda.synchronize()
+    assert torch.equal(dout, ref)
+    want = (dout.float() * o.float()).view(T, H, HD).sum(-1).t().contiguous()          # [H, T]
+    got = dvec.view(H, T)
+    assert (got - want).abs().max().item() <= 1e-4 * want.abs().max().item() + 1e-5
+    a = ops.attn_bwd(qkv, o, dout, lse, cu, seqlens, H)
+    b = ops.attn_bwd(qkv, o, dout, lse, cu, seqlens, H, dvec=dvec)
+    torch.cuda.synchronize()
+    assert (a.float() - b.float()).abs().max().item() <= 2e-2 * a.float().abs().max().item()
+    assert (a == b).float().mean().item() > 0.99                                        # identical except where D's rounding moved a bf16 ulp
