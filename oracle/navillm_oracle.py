@@ -324,7 +324,8 @@ def _lm_labels(text):
     return labels
 
 
-def forward_summarization(sd: SD, cfg: OracleConfig, batch, tokenize, eos_token: str, training=True, max_new_tokens=50):
+def forward_summarization(sd: SD, cfg: OracleConfig, batch, tokenize, eos_token: str, training=True, max_new_tokens=50,
+                          trie=None, eos_token_id=2, pad_token_id=0):
     """NavModel.forward_summarization (models/nav_model.py:251-343), training branch and greedy branch."""
     vp = batch["vp_img_embeds"][:, 1:, :]                                                      # remove stop :267-268
     nav_masks = batch["vp_nav_masks"][:, 1:]
@@ -343,8 +344,10 @@ def forward_summarization(sd: SD, cfg: OracleConfig, batch, tokenize, eos_token:
         out = modified_lm_forward(sd, cfg, text["input_ids"], text["attention_mask"], labels=_lm_labels(text),
                                   cand_vis=vp[nav_masks], hist_vis=hist_vis_input)
         return {"loss": out["loss"]}
+    procs = [TrieLogitsProcessor(trie)] if trie is not None else []              # models/nav_model.py:321-322
     ids = greedy_generate(sd, cfg, text["input_ids"], text["attention_mask"], cand_vis=vp[nav_masks],
-                          hist_vis=hist_vis_input, max_new_tokens=max_new_tokens)
+                          hist_vis=hist_vis_input, max_new_tokens=max_new_tokens, eos_token_id=eos_token_id,
+                          pad_token_id=pad_token_id, logits_processor=procs)
     return {"generated_ids": ids[:, text["input_ids"].shape[1]:]}
 
 
@@ -391,8 +394,29 @@ def forward_object_grounding(sd: SD, cfg: OracleConfig, batch, tokenize):
 # Greedy decode (HF GenerationMixin greedy search semantics; models/modified_lm.py:184-199,
 # models/nav_model.py:324-338,388-399).  Restated: see module docstring.
 # =====================================================================================================
+class TrieLogitsProcessor:
+    """models/modified_lm.py:10-30: per-row walk of a Trie (tools/trie.py interface: root, get_next_node,
+    get_child_index); every token that is not a child of the row's current node is masked to -inf."""
+
+    def __init__(self, trie):
+        self.node_states, self.trie = None, trie
+
+    def __call__(self, input_ids, scores):
+        B = input_ids.shape[0]
+        if self.node_states is None:
+            self.node_states = [self.trie.root for _ in range(B)]
+        else:
+            for bn in range(B):
+                self.node_states[bn] = self.trie.get_next_node(self.node_states[bn], int(input_ids[bn, -1]))
+        masks = torch.zeros_like(scores, dtype=torch.bool)
+        for bn in range(B):
+            masks[bn][self.trie.get_child_index(self.node_states[bn])] = True
+        return scores.masked_fill(~masks, float("-inf"))
+
+
 def greedy_generate(sd: SD, cfg: OracleConfig, input_ids, attention_mask, cand_vis=None, hist_vis=None, obj_vis=None,
-                    max_new_tokens=20, eos_token_id=2, pad_token_id=0, stop_on_eos=True, return_logits=False):
+                    max_new_tokens=20, eos_token_id=2, pad_token_id=0, stop_on_eos=True, return_logits=False,
+                    logits_processor=None):
     B = input_ids.shape[0]
     ids = input_ids.clone()
     mask = attention_mask.clone()
@@ -407,6 +431,8 @@ def greedy_generate(sd: SD, cfg: OracleConfig, input_ids, attention_mask, cand_v
         else:
             out = modified_lm_forward(sd, cfg, ids[:, -1:], mask, position_ids=pos[:, -1:], past_kv=past)
         logits = out["logits"][:, -1, :].float()
+        for proc in (logits_processor or []):            # HF applies the processors to the next-token scores
+            logits = proc(ids, logits)
         if return_logits:
             step_logits.append(logits)
         nxt = logits.argmax(dim=-1)

@@ -53,9 +53,25 @@ def main():
         with torch.no_grad():
             sent = model("3dqa", dict(gold["qa_in"]), training=False, max_new_tokens=10, do_sample=False)["generated_sentences"]
         out.update(ids=captured["ids"], prompt_len=captured["prompt_len"], sentences=sent)
+        # summarization generation branch (models/nav_model.py:320-341): <hist> + <cand> visual tokens, max_new_tokens=50
+        # fixed by the reference, greedy; once free and once constrained by a Trie (tools/trie.py; caller
+        # tasks/agents/mp3d_agent.py:545-556 builds it from the candidate answers)
+        from tools.trie import Trie
+        tok = model.lang_model.tokenizer
+        with torch.no_grad():
+            s_free = model("summarization", dict(gold["sum_in"]), training=False)["generated_sentences"]
+        out.update(sum_ids=captured["ids"], sum_prompt_len=captured["prompt_len"], sum_sentences=s_free)
+        words = [[21, 22, 23], [21, 22, 30, 31], [21, 40], [50, 51, 52]]
+        trie = Trie(tok.bos_token_id, tok.eos_token_id)
+        for w in words:
+            trie.insert(w)
+        with torch.no_grad():
+            s_trie = model("summarization", dict(gold["sum_in"]), training=False, trie=trie)["generated_sentences"]
+        out.update(trie_words=words, trie_ids=captured["ids"], trie_sentences=s_trie)
         path = Path(__file__).resolve().parent / f"generate_{precision}.pt"
         torch.save(out, path)
-        print("wrote", path, captured["ids"][:, captured["prompt_len"]:].tolist(), sent)
+        print("wrote", path, out["ids"][:, out["prompt_len"]:].tolist(), "| sum:", out["sum_ids"][:, out["sum_prompt_len"]:][:, :8].tolist(),
+              "| trie:", out["trie_ids"][:, out["sum_prompt_len"]:].tolist())
 
 
 if __name__ == "__main__":

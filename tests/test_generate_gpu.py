@@ -175,3 +175,21 @@ def test_3dqa_generation_matches_reference_generation_branch(cuda_dev):
             assert (top2[0] - top2[1]).item() <= 2 * 2.0 ** -8 * top2[0].abs().item(), (b, t, mine, ref)
             break
         assert mt[:4] == rt[:4], (mine, ref)
+
+
+def test_summarization_generation_branch_matches_reference(cuda_dev):
+    """model('summarization', training=False[, trie=...]) on the kernels against sentences produced by the reference's own
+    generation branch (models/nav_model.py:320-341; tests/golden/generate_amp_bf16.pt): the Trie-constrained rows must be
+    identical; the free rows identical up to the first bf16 near-tie (checked on the first tokens)."""
+    from tests.test_navmodel_gpu import build_model, to_dev
+    g = torch.load(GOLD / "nav_amp_bf16.pt", weights_only=False)
+    gen = torch.load(GOLD / "generate_amp_bf16.pt", weights_only=False)
+    model, tok = build_model(g, cuda_dev)
+    trie = _Trie(tok.bos_token_id, tok.eos_token_id)
+    for w in gen["trie_words"]:
+        trie.insert(w)
+    out = model("summarization", to_dev(dict(g["sum_in"]), cuda_dev), training=False, trie=trie)["generated_sentences"]
+    assert out == gen["trie_sentences"], (out, gen["trie_sentences"])
+    free = model("summarization", to_dev(dict(g["sum_in"]), cuda_dev), training=False)["generated_sentences"]
+    for mine, ref in zip(free, gen["sum_sentences"]):
+        assert mine.split()[:5] == ref.split()[:5], (mine, ref)

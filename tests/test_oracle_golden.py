@@ -176,3 +176,51 @@ def test_greedy_generate_matches_reference_generation_branch(precision):
         else:
             continue
     assert torch.equal(ids[:, S0:S0 + 4], gen["ids"][:, S0:S0 + 4])          # the first tokens are far from ties
+
+
+class _Node:
+    def __init__(self):
+        from collections import defaultdict
+        self.child = defaultdict(_Node)
+
+
+class _Trie:
+    """tools/trie.py interface."""
+
+    def __init__(self, bos, eos):
+        self.root, self.bos, self.eos = _Node(), bos, eos
+
+    def insert(self, word):
+        cur = self.root
+        for c in word:
+            cur = cur.child[c]
+
+    def get_child_index(self, cur):
+        return [self.eos] if len(cur.child) == 0 else list(cur.child.keys())
+
+    def get_next_node(self, cur, w):
+        return cur if len(cur.child) == 0 else cur.child[w]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "amp_bf16"])
+def test_summarization_generation_branch_matches_reference(precision):
+    """Oracle vs the reference's summarization generation branch (models/nav_model.py:320-341): <hist> and <cand> visual
+    tokens, 50 new tokens, free and Trie-constrained (TrieLogitsProcessor, models/modified_lm.py:10-30)."""
+    g, cfg, tok = load(precision)
+    gen = torch.load(GOLD / f"generate_{precision}.pt", weights_only=False)
+    sd = g["state_dict"]
+    S0 = gen["sum_prompt_len"]
+    trie = _Trie(tok.bos_token_id, tok.eos_token_id)
+    for w in gen["trie_words"]:
+        trie.insert(w)
+    out = O.forward_summarization(sd, cfg, g["sum_in"], tok, tok.eos_token, training=False, trie=trie,
+                                  eos_token_id=tok.eos_token_id, pad_token_id=tok.unk_token_id)["generated_ids"]
+    assert out.tolist() == gen["trie_ids"][:, S0:].tolist()
+    free = O.forward_summarization(sd, cfg, g["sum_in"], tok, tok.eos_token, training=False,
+                                   eos_token_id=tok.eos_token_id, pad_token_id=tok.unk_token_id)["generated_ids"]
+    ref = gen["sum_ids"][:, S0:]
+    n = min(free.shape[1], ref.shape[1])
+    if precision == "fp32":
+        assert free[:, :n].tolist() == ref[:, :n].tolist()
+    else:
+        assert free[:, :5].tolist() == ref[:, :5].tolist()                   # later steps may hit a bf16 near-tie
