@@ -21,6 +21,7 @@
 #include "nv_common.cuh"
 #include "nv_host.h"
 #include <cstdlib>
+#include <mutex>
 
 namespace nv {
 
@@ -560,12 +561,17 @@ gemm_bf16_tcgen05_2cta(const __grid_constant__ CUtensorMap tmap_a, const __grid_
   }
 }
 
-// One self-resetting claim counter per (device, stream hash): kernels on one stream never overlap, so they can share
-// it.  NV_GEMM_STATIC_SCHED=1 selects the static schedule (A/B measurements).
+// One self-resetting claim counter per (device, stream): kernels on one stream never overlap, so they can share it;
+// different streams get different counters (exact table, no hashing: a collision would let two concurrent GEMMs
+// corrupt each other's tile claims).  NV_GEMM_STATIC_SCHED=1 selects the static schedule (A/B measurements).
 static int tile_counter_for(cudaStream_t stream, uint32_t** out) {
   constexpr int SLOTS = 64, MAX_DEV = 16;
   static uint32_t* pool[MAX_DEV] = {nullptr};
+  static cudaStream_t owner[MAX_DEV][SLOTS];
+  static int used[MAX_DEV] = {0};
+  static std::mutex mu;
   static int static_sched = -1;
+  std::lock_guard<std::mutex> lock(mu);
   if (static_sched < 0) {
     const char* e = getenv("NV_GEMM_STATIC_SCHED");
     static_sched = (e && e[0] == '1') ? 1 : 0;
@@ -579,8 +585,15 @@ static int tile_counter_for(cudaStream_t stream, uint32_t** out) {
     NV_CUDA(cudaMalloc(&pool[dev], SLOTS * 128));      // one counter per 128-byte line
     NV_CUDA(cudaMemset(pool[dev], 0, SLOTS * 128));
   }
-  const uint64_t h = (reinterpret_cast<uint64_t>(stream) >> 4) * 0x9E3779B97F4A7C15ull;
-  *out = pool[dev] + (h >> 58) * 32;
+  int slot = -1;
+  for (int i = 0; i < used[dev]; ++i)
+    if (owner[dev][i] == stream) { slot = i; break; }
+  if (slot < 0) {
+    if (used[dev] == SLOTS) return NV_OK;              // more streams than counters: static schedule for the extra ones
+    slot = used[dev]++;
+    owner[dev][slot] = stream;
+  }
+  *out = pool[dev] + slot * 32;
   return NV_OK;
 }
 
