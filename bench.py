@@ -214,10 +214,49 @@ def cpu_reference_sample(n_layers: int, seq: int, reps: int = 1, warm: int = 1):
     return best
 
 
+_CPU_THREADS = None
+
+
+def pick_cpu_threads() -> int:
+    """Thread count that gives the CPU arm its best throughput on this host: os.cpu_count() can exceed what the container
+    may use (affinity mask, cgroup quota) and oversubscribed intra-op threads run torch's GEMMs many times slower.  The
+    candidates are probed with the layer's own GEMM shape (a few hundred ms in total) and the fastest one is kept."""
+    global _CPU_THREADS
+    if _CPU_THREADS is not None:
+        return _CPU_THREADS
+    cands = {os.cpu_count() or 1}
+    if hasattr(os, "sched_getaffinity"):
+        cands.add(len(os.sched_getaffinity(0)))
+    for path, parse in (("/sys/fs/cgroup/cpu.max", lambda t: None if t.split()[0] == "max" else int(t.split()[0]) / int(t.split()[1])),
+                        ("/sys/fs/cgroup/cpu/cpu.cfs_quota_us", lambda t: None if int(t) <= 0 else int(t) / 100000.0)):
+        try:
+            q = parse(Path(path).read_text())
+            if q:
+                cands.add(max(1, int(q)))
+        except Exception:
+            pass
+    top = max(cands)
+    cands |= {t for t in (8, 16, 32, 64, 128) if t <= top}
+    a = torch.randn(640, D_MODEL)
+    w = torch.randn(D_MODEL, D_MODEL)
+    best, best_t = None, None
+    for t in sorted(cands):
+        torch.set_num_threads(t)
+        a @ w
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ w
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best, best_t = t, dt
+    torch.set_num_threads(best)
+    _CPU_THREADS = best
+    return best
+
+
 def _cpu_reference_sample(n_layers: int, seq: int, reps: int, warm: int, dtype):
     from oracle import navillm_oracle as O
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    cores = pick_cpu_threads()
     cfg = O.OracleConfig(hidden=D_MODEL, n_layers=n_layers, n_heads=N_HEADS, inter=D_FF, vocab=64,
                          precision="amp_bf16" if dtype == torch.bfloat16 else "fp32")
     g = torch.Generator().manual_seed(0)
