@@ -114,6 +114,97 @@ __global__ void __launch_bounds__(192, 1) ts_kernel(float* out_ss, float* out_ts
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// Probe of the TMEM A-operand layout (run when the hypothesis above fails): TMEM cell (row r, 32-bit column c) holds the
+// bf16 pair (1 + 2c, 2 + 2c) [probe 0] or (r, r) for r < 128 [probe 1]; B = identity (B[n][k] = delta(n, k), N = K = 64).
+// Then D[m][n] = the value the tensor core read as A[m][k = n]: probe 0 names the (column, half) feeding each k, probe 1
+// names the TMEM lane feeding each output row.
+template <int PROBE>
+__global__ void __launch_bounds__(192, 1) probe_kernel(float* out) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 64 * 128);
+  uint32_t* tptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
+  for (uint32_t i = threadIdx.x; i < 64 * 8; i += blockDim.x) {
+    const uint32_t r = i >> 3, c = i & 7;
+    uint32_t w[4];
+    for (uint32_t q = 0; q < 4; ++q)
+      w[q] = pack_bf16x2(r == c * 8 + 2 * q ? 1.f : 0.f, r == c * 8 + 2 * q + 1 ? 1.f : 0.f);
+    *reinterpret_cast<uint4*>(sB + sw128_offset(r, c)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (warp == 0) { tmem_alloc(tptr, 512); tmem_relinquish(); }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tptr, tD = tmem, tA = tmem + 256;
+  if (warp >= 2) {
+    const uint32_t r = (warp & 3) * 32 + lane;
+    uint32_t v[32];
+#pragma unroll
+    for (uint32_t c = 0; c < 32; ++c)
+      v[c] = PROBE == 0 ? pack_bf16x2((float)(1 + 2 * c), (float)(2 + 2 * c)) : pack_bf16x2((float)r, (float)r);
+    tmem_st_32x32b_x32(tA + (((warp & 3) * 32) << 16), v);
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  constexpr uint32_t idesc = umma_idesc_bf16(128, 64, 0, 0);
+  const uint64_t bd = umma_smem_desc_sw128(smem_u32(sB), 0, 1024);
+  if (warp == 1) {
+    if (elect_one()) {
+#pragma unroll
+      for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ts(tD, tA + ks * 8, bd + ks * 2, idesc, ks ? 1u : 0u);
+      umma_commit(bar);
+    }
+    __syncwarp();
+  }
+  if (warp >= 2) {
+    mbar_wait(bar, 0);
+    tc_fence_after();
+    const uint32_t r = (warp & 3) * 32 + lane;
+    for (uint32_t c = 0; c < 64; c += 32) {
+      uint32_t a[32];
+      tmem_ld_32x32b_x32(tD + (((warp & 3) * 32) << 16) + c, a);
+      tmem_ld_wait();
+      for (uint32_t j = 0; j < 32; ++j) out[r * 64 + c + j] = __uint_as_float(a[j]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int PROBE>
+void probe() {
+  float* out;
+  cudaMalloc(&out, 128 * 64 * 4);
+  auto k = probe_kernel<PROBE>;
+  const int smem = 64 * 128 + 64 + 1024;
+  k<<<1, 192, smem>>>(out);
+  cudaError_t e = cudaDeviceSynchronize();
+  static float h[128 * 64];
+  cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+  printf("probe %d (%s)  %s\n", PROBE, PROBE == 0 ? "value 1+2c+half read as k, rows 0, 1, 37, 64, 100" : "TMEM lane read as output row m (column 0), all rows",
+         e == cudaSuccess ? "" : cudaGetErrorString(e));
+  if (PROBE == 0) {
+    const int rows[5] = {0, 1, 37, 64, 100};
+    for (int ri = 0; ri < 5; ++ri) {
+      printf("  row %3d:", rows[ri]);
+      for (int n = 0; n < 64; ++n) printf(" %g", h[rows[ri] * 64 + n]);
+      printf("\n");
+    }
+  } else {
+    printf("  ");
+    for (int m = 0; m < 128; ++m) printf(" %g", h[m * 64]);
+    printf("\n");
+  }
+  cudaFree(out);
+}
+
 template <uint32_t N>
 void run() {
   float *ss, *ts;
@@ -151,5 +242,7 @@ void run() {
 int main() {
   run<64>();
   run<128>();
+  probe<0>();
+  probe<1>();
   return 0;
 }
