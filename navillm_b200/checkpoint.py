@@ -8,7 +8,7 @@
   its flat moment buffers in ``model.parameters()`` order).
 * ``FeatureStore``: a memory-mapped replacement for the per-access ``h5py.File`` open + fp64->fp32 cast of
   ``ImageFeaturesDB.get_image_feature`` (tasks/feature_db.py:18-31), which becomes the input bottleneck once a navigation
-  step takes milliseconds: one contiguous fp16 (or fp32) block file + a JSON index; ``get_image_feature(scan, viewpoint)``
+  step takes milliseconds: one contiguous fp32 (opt-in fp16: values rounded to half precision) block file + a JSON index; ``get_image_feature(scan, viewpoint)``
   returns the same ``float32 [n_views, image_feat_size]`` slice.  ``FeatureStore.convert_hdf5`` builds it from the
   reference's HDF5 files when h5py is available (it is not in the build image; ``FeatureStore.build`` takes any
   ``(key, array)`` iterable)."""
@@ -91,7 +91,7 @@ class FeatureStore:
         return ft
 
     @staticmethod
-    def build(path: str, items: Iterable[Tuple[str, np.ndarray]], dtype: str = "float16") -> "None":
+    def build(path: str, items: Iterable[Tuple[str, np.ndarray]], dtype: str = "float32") -> "None":
         index, off, dim = {}, 0, None
         with open(str(path) + ".bin", "wb") as f:
             for key, arr in items:
@@ -108,7 +108,7 @@ class FeatureStore:
         Path(str(path) + ".json").write_text(json.dumps({"dtype": dtype, "dim": dim, "index": index}))
 
     @staticmethod
-    def convert_hdf5(h5_path: str, out_path: str, dtype: str = "float16") -> None:
+    def convert_hdf5(h5_path: str, out_path: str, dtype: str = "float32") -> None:
         try:
             import h5py
         except ImportError as e:  # pragma: no cover - h5py is not part of the build image

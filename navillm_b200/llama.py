@@ -74,9 +74,12 @@ class _Attn(nn.Module):
 class _MLP(nn.Module):
     def __init__(self, d: LlamaDims, dtype):
         super().__init__()
+        # registration order of transformers==4.28.0's LlamaMLP (gate, down, up): torch.optim state indices of reference
+        # checkpoints follow model.parameters() order (tools/optims.py:43,69-71).  The fused gate|up weight view depends
+        # only on the flat-buffer order (ModifiedLlamaForCausalLM.lm_parameters), not on this one.
         self.gate_proj = _Linear(d.inter, d.hidden, dtype=dtype)
-        self.up_proj = _Linear(d.inter, d.hidden, dtype=dtype)
         self.down_proj = _Linear(d.hidden, d.inter, dtype=dtype)
+        self.up_proj = _Linear(d.inter, d.hidden, dtype=dtype)
 
 
 class _Layer(nn.Module):

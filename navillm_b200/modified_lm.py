@@ -24,6 +24,7 @@ import torch.nn as nn
 from . import llama as llama_mod
 from . import ops
 from .llama import FlatParams, LlamaCore, LlamaDims, LlamaModelParams, _Linear, init_llama_params_
+from .parallel import GradSync
 from .tokenizer import SPECIAL_TOKENS, HFTokenizerAdapter, SyntheticTokenizer
 
 bf16 = torch.bfloat16
@@ -221,6 +222,7 @@ class _LMFn(torch.autograd.Function):
         lm, pp = ctx.lm, ctx.pp
         core, d = lm.core, lm.dims
         normw = lm.model.norm.weight
+        lm.grad_sync.backward_begins()               # first custom node of the pass in the LM-loss modes (no-op if queued)
         if ctx.mode == "rows":
             g, rstd = ctx.saved
             dy = dout.contiguous().to(bf16)
@@ -259,14 +261,27 @@ class ModifiedLlamaForCausalLM(nn.Module):
         self.core: Optional[LlamaCore] = None
         self.training_enabled = True
         self.register_buffer("_anchor", torch.zeros((), dtype=torch.float32), persistent=False)
+        self.grad_sync = GradSync()                  # replaced by NavModel's shared state when owned by a NavModel
+        self.grad_sync.flats = self._own_flats
         if tokenizer is not None:
             self._set_tokenizer(tokenizer)
 
     # ---- tokenizer front-end (models/modified_lm.py:56-87) ----
-    def init_tokenizer(self, pretrained_model_name_or_path: Optional[str]):
+    def init_tokenizer(self, pretrained_model_name_or_path: Optional[str], allow_synthetic: bool = False):
+        """The reference's tokenizer construction (models/modified_lm.py:56-75) from a LOCAL tokenizer directory.  Without
+        usable tokenizer files this raises: pretrained / resumed Vicuna weights on hash-derived token ids would run
+        silently on garbage.  ``allow_synthetic=True`` (from-scratch runs, tests, benches) falls back to the deterministic
+        ``SyntheticTokenizer`` and says so."""
         try:
             tok = HFTokenizerAdapter(pretrained_model_name_or_path)
-        except Exception:
+        except Exception as e:
+            if not allow_synthetic:
+                raise RuntimeError(f"no usable LLaMA tokenizer under {pretrained_model_name_or_path!r} ({type(e).__name__}: {e}); "
+                                   f"pass a local tokenizer directory, or model_config.tokenizer / --from_scratch for the "
+                                   f"synthetic stand-in") from e
+            import warnings
+            warnings.warn(f"navillm_b200: no tokenizer files under {pretrained_model_name_or_path!r}; using SyntheticTokenizer "
+                          f"(word-hash ids) -- only meaningful with randomly initialised weights")
             tok = SyntheticTokenizer(base_vocab=self.dims.vocab if self.dims.vocab < 32000 else 32000)
         self._set_tokenizer(tok)
 
@@ -328,59 +343,18 @@ class ModifiedLlamaForCausalLM(nn.Module):
     def _device(self) -> torch.device:
         return self.model.norm.weight.device
 
-    # ---- data-parallel gradient exchange overlapped with the backward ----
-    sync_grads = True            # False inside NavModel.no_sync()
-    overlap_grad_reduce = True
-    reduce_chunk_layers = 4
-
+    # ---- data-parallel gradient exchange (navillm_b200/parallel.py) ----
     def _grad_sync_hook(self):
-        """Returns a per-layer callback for LlamaCore.backward that all-reduces (AVG) the flat-gradient slice of
-        every finished group of ``reduce_chunk_layers`` layers asynchronously: NCCL waits only for the kernels
-        enqueued so far and runs while the remaining layers' backward GEMMs execute.  None when not applicable."""
-        import torch.distributed as dist
-        if not (self.sync_grads and self.overlap_grad_reduce and dist.is_available() and dist.is_initialized()
-                and dist.get_world_size() > 1):
-            return None
-        flat, layers, n = self.flat, self.model.layers, self.dims.n_layers
+        """Per-layer callback for LlamaCore.backward that all-reduces (AVG) the flat-gradient slice of every finished
+        group of decoder layers asynchronously, so NCCL runs while the remaining layers' backward GEMMs execute.  Only
+        an ARMED pass gets one (a forward outside ``no_sync()`` through the DDP wrapper, see ``GradSync``): a backward
+        inside ``no_sync`` issues no collective, whatever the other ranks are doing."""
+        flat, layers = self.flat, self.model.layers
         starts = [flat.offset_of(l.self_attn.q_proj.weight) for l in layers] + [flat.offset_of(self.model.embed_tokens.weight)]
-        chunk = max(1, self.reduce_chunk_layers)
-        self._pending_reduces = []
-        self._layers_reduced = True
-        avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
-        ws = dist.get_world_size()
+        return self.grad_sync.layer_hook(flat, starts, self.dims.n_layers)
 
-        def done(l):
-            if l % chunk != 0:
-                return
-            hi = min(l + chunk, n)
-            sl = flat.flat_grad[starts[l]:starts[hi]]
-            h = dist.all_reduce(sl, op=avg, async_op=True)
-            self._pending_reduces.append((h, sl if avg == dist.ReduceOp.SUM else None, ws))
-        return done
-
-    def finish_grad_sync(self) -> int:
-        """Wait for the overlapped layer reductions and reduce what they did not cover (embeddings, final norm,
-        lm_head, heads).  Returns the number of collectives issued here."""
-        import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return 0
-        ws = dist.get_world_size()
-        avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
-        pend = getattr(self, "_pending_reduces", [])
-        for h, sl, _ in pend:
-            h.wait()
-            if sl is not None:
-                sl.div_(ws)
-        self._pending_reduces = []
-        if getattr(self, "_layers_reduced", False):
-            tail = self.flat.flat_grad[self.flat.offset_of(self.model.embed_tokens.weight):]
-            self._layers_reduced = False
-        else:
-            tail = self.flat.flat_grad
-        dist.all_reduce(tail, op=avg)
-        if avg == dist.ReduceOp.SUM:
-            tail.div_(ws)
-        return 1
+    def _own_flats(self):
+        return [(self.flat, self.flat.offset_of(self.model.embed_tokens.weight))] if self.core is not None else []
 
     def _ensure(self):
         dev = self._device()
@@ -462,6 +436,14 @@ class ModifiedLlamaForCausalLM(nn.Module):
     # ---- reference-compatible forward (models/modified_lm.py:89-146) ----
     def forward(self, input_ids, attention_mask, labels=None, cand_vis=None, hist_vis=None, obj_vis=None,
                 return_logits: bool = False, **kwargs):
+        """One full-prompt pass.  ``hidden_states`` is the reference's [B, S, D] tensor (zeros at pad positions, which the
+        reference fills with values nothing reads); ``logits`` ([B, S, V] with the special tokens at -inf) only on request
+        (``return_logits=True``): every caller on the path reads ``loss`` or ``hidden_states``.
+        Incremental decoding arguments are not accepted here -- the KV-cache loop lives in ``generate``."""
+        for k in ("past_key_values", "position_ids", "inputs_embeds"):
+            if kwargs.get(k) is not None:
+                raise NotImplementedError(f"ModifiedLlamaForCausalLM.forward({k}=...) is not supported: use .generate() for "
+                                          f"incremental decoding (HF's generate loop is replaced by a native KV-cache loop)")
         self._ensure()
         dev = self._device()
         pp = PackedPrompt(input_ids, attention_mask, self, dev, labels=labels)
@@ -486,7 +468,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
     def generate(self, input_ids, attention_mask, cand_vis=None, hist_vis=None, obj_vis=None, max_new_tokens: int = 20,
                  do_sample: bool = False, temperature: float = 1.0, eos_token_id: Optional[int] = None,
                  pad_token_id: Optional[int] = None, bos_token_id: Optional[int] = None, logits_processor=None, trie=None,
-                 stop_on_eos: bool = True, use_cuda_graph: bool = True, **unused) -> torch.Tensor:
+                 stop_on_eos: bool = True, use_cuda_graph: bool = True, stats: Optional[dict] = None, **unused) -> torch.Tensor:
         """Prefill on the packed kernels (positions = cumsum(mask)-1 like HF generate; visual tokens injected only
         here, as in models/modified_lm.py:195-197), then one token per step over a pre-allocated KV cache.  The
         greedy step has static shapes and is replayed as a CUDA graph.  Returns [B, S0 + n_new] int64 ids (prompt
@@ -496,6 +478,10 @@ class ModifiedLlamaForCausalLM(nn.Module):
         core, d = self.core, self.dims
         eos = self.tokenizer.eos_token_id if eos_token_id is None else eos_token_id
         pad = self.tokenizer.unk_token_id if pad_token_id is None else pad_token_id
+        ev = None
+        if stats is not None:                                     # bench.py: device-side phase times (forces one sync at the end)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         pp = PackedPrompt(input_ids, attention_mask, self, dev, generate_positions=True)
         vis = self.cat_vis(cand_vis, hist_vis, obj_vis, pp)
         B, H, D = pp.B, d.n_heads, d.hidden
@@ -557,9 +543,11 @@ class ModifiedLlamaForCausalLM(nn.Module):
             next_ids.copy_(nxt.to(torch.int32))
 
         head(hid_last)
-        host_ids = [row.tolist() for row in input_ids.cpu()]
+        host_ids = [row.tolist() for row in input_ids.cpu()] if not greedy else None
         pick(host_ids)
         out_tokens = [next_ids.clone()]
+        if ev is not None:
+            ev[1].record()
 
         def step():
             xt = ops.embed_fwd(next_ids, E)
@@ -567,9 +555,13 @@ class ModifiedLlamaForCausalLM(nn.Module):
             head(h)
             ops.add_int_(lens, 1)
 
-        graph = None
+        # HF stops when every sequence has finished.  Asking the device after EVERY token would serialise host and device
+        # (one blocking read per token); finished rows only emit pad tokens, so the greedy loop looks every `check_every`
+        # tokens and the surplus pad columns are trimmed below -- same ids as a per-token check.
+        check_every = 8 if greedy else 1
+        graph, replays = None, 0
         for it in range(1, max_new_tokens):
-            if stop_on_eos and bool(finished.all()):              # HF stops when every sequence has finished
+            if stop_on_eos and it % check_every == 0 and bool(finished.all()):
                 break
             if not greedy:
                 for bn, t in enumerate(out_tokens[-1].tolist()):
@@ -583,11 +575,26 @@ class ModifiedLlamaForCausalLM(nn.Module):
                     with torch.cuda.graph(graph):
                         step()
                         ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)
+                    if ev is not None:
+                        ev[2].record()
                     continue
                 graph.replay()
+                replays += 1
             else:
                 step()
                 pick(host_ids)
             out_tokens.append(next_ids.clone())
+        if ev is not None:
+            ev[3].record()
+            torch.cuda.synchronize()
+            stats.update({"prefill_ms": ev[0].elapsed_time(ev[1]), "graph_replays": replays,
+                          "decode_ms": ev[2].elapsed_time(ev[3]) if (graph is not None and replays > 0) else None,
+                          "kv_rows": Smax, "prompt_lens": list(pp.seqlens)})
         new = torch.stack(out_tokens, dim=1).to(torch.int64)
+        if stop_on_eos and greedy and new.shape[1] > 1:
+            # trim the columns generated after the step at which the last row emitted EOS (see check_every above)
+            is_eos = (new == eos)
+            if bool(is_eos.any(dim=1).all()):
+                last = int(is_eos.float().argmax(dim=1).max())        # first EOS per row; the slowest row decides
+                new = new[:, :last + 1]
         return torch.cat([input_ids.to(dev), new], dim=1)

@@ -26,6 +26,7 @@ from . import ops
 from .image_embedding import ImageEmbeddings, _grad, _lin_bwd, _lin_fwd, _ln_bwd, _ln_fwd
 from .llama import FlatParams
 from .modified_lm import LMOutput, ModifiedLlamaForCausalLM, PackedPrompt
+from .parallel import GradSync
 
 bf16 = torch.bfloat16
 f32 = torch.float32
@@ -134,19 +135,21 @@ class _HeadFn(torch.autograd.Function):
     scatter with -inf elsewhere (:239-242) when ``slot`` is given, or the raw [B,100] predictions."""
 
     @staticmethod
-    def forward(ctx, lin: nn.Linear, h, slot, B, G):
+    def forward(ctx, lin: nn.Linear, h, slot, B, G, sync=None):
         pred = ops.head_fwd(h.contiguous(), lin.weight.data, lin.bias.data)
-        ctx.lin, ctx.saved = lin, (h, slot, pred.shape[1])
+        ctx.lin, ctx.saved, ctx.sync = lin, (h, slot, pred.shape[1]), sync
         return ops.logit_scatter_fwd(pred, slot, B, G) if slot is not None else pred
 
     @staticmethod
     def backward(ctx, dout):
         h, slot, O = ctx.saved
         lin = ctx.lin
+        if ctx.sync is not None:
+            ctx.sync.backward_begins()               # first custom node of a navigation / grounding backward pass
         dout = dout.contiguous().to(bf16)
         dpred = ops.logit_scatter_bwd(dout, slot, O) if slot is not None else dout
         dh = ops.head_bwd(dpred, h.contiguous(), lin.weight.data, dW=lin.weight.grad, db=lin.bias.grad)
-        return None, dh, None, None, None
+        return None, dh, None, None, None, None
 
 
 class NavModel(nn.Module):
@@ -172,7 +175,7 @@ class NavModel(nn.Module):
         if tok is not None:
             self.lang_model._set_tokenizer(tok)
         else:
-            self.lang_model.init_tokenizer(config.pretrained_model_name_or_path)
+            self.lang_model.init_tokenizer(config.pretrained_model_name_or_path, allow_synthetic=bool(args.from_scratch))
 
         self.hidden_size = self.lang_model.hidden_size
         self.model_type = self.lang_model.model_type
@@ -202,7 +205,10 @@ class NavModel(nn.Module):
         self.history = None
         self.hist_vis = None
         self._flat32: Optional[FlatParams] = None
-        self._sync_grads = True
+        # data-parallel gradient exchange: ONE state shared with the language model (navillm_b200/parallel.py)
+        self.grad_sync = GradSync()
+        self.grad_sync.flats = self._sync_flats
+        self.lang_model.grad_sync = self.grad_sync
         if logger is not None:
             logger.info("model type: {}".format(self.model_type))
 
@@ -237,23 +243,37 @@ class NavModel(nn.Module):
         elif f.params[0].grad is None or f.params[0].grad.data_ptr() != f.flat_grad.data_ptr():
             f.reattach_grads()
 
+    def _flat_buffers_ready(self) -> bool:
+        return self.lang_model.core is not None and self._flat32 is not None
+
+    def _sync_flats(self):
+        """[(flat buffer, offset where the part NOT covered by the overlapped LM layer reductions starts)]."""
+        if not self._flat_buffers_ready():
+            return []
+        self._settle_lazy_zero()
+        lm = self.lang_model
+        return [(lm.flat, lm.flat.offset_of(lm.model.embed_tokens.weight)), (self._flat32, None)]
+
+    def _settle_lazy_zero(self) -> None:
+        """``zero_grad(lazy=True)`` promised that the next LM backward overwrites the per-layer gradients.  If an
+        exchange or an optimizer step arrives with no LM backward in between (a skipped / guarded iteration), the stale
+        values must not be applied: make the promise true by zero-filling now."""
+        lm = self.lang_model
+        if lm.core is not None and getattr(lm.flat, "overwrite_layer_grads", False):
+            lm.flat.flat_grad[:lm.flat.offset_of(lm.model.embed_tokens.weight)].zero_()
+            lm.flat.overwrite_layer_grads = False
+
     @contextlib.contextmanager
     def no_sync(self):
-        """DDP-compatible context (tasks/agents/mp3d_agent.py:661-667): gradients accumulate locally; the
-        all-reduce is issued by ``allreduce_grads`` on the first backward outside this context."""
-        old = self._sync_grads
-        self._sync_grads = self.lang_model.sync_grads = False
-        try:
-            yield
-        finally:
-            self._sync_grads = self.lang_model.sync_grads = old
+        """Bare (unwrapped) use only: marks passes whose gradients stay local.  A bare NavModel never exchanges gradients
+        on its own -- call ``allreduce_grads()`` after the last backward, or wrap the model in
+        ``navillm_b200.parallel.DistributedDataParallel`` for the reference's DDP behaviour (tools/optims.py:52-54)."""
+        yield
 
     def allreduce_grads(self, average: bool = True):
-        """ONE NCCL all-reduce per dtype over the flat gradient buffers (replaces DDP's
-        bucketed reduction of tools/optims.py:52-54).  No-op without an initialised process group."""
-        from .llama import allreduce_flat_grads
-        n = self.lang_model.finish_grad_sync()           # LM buffer: layer slices were reduced during the backward
-        return n + allreduce_flat_grads([self._flat32], average=average)
+        """Explicit exchange for bare use: ONE all-reduce (average) per flat gradient buffer.  No-op
+        without an initialised multi-rank process group.  Returns the number of collectives issued."""
+        return self.grad_sync.exchange()
 
     def zero_grad(self, set_to_none: bool = False, lazy: bool = False):
         """Gradients live in two flat buffers, so zeroing is two fills instead of one per parameter.  With
@@ -384,7 +404,7 @@ class NavModel(nn.Module):
             if pp.n_cls != B:
                 raise RuntimeError(f"expected one <cls_1> token per prompt, found {pp.n_cls} in {B} prompts")
             h_cls = self.lang_model.hidden_rows(pp, vis, pp.cls_rows)
-        fuse_logits = _HeadFn.apply(self.out_head[0], h_cls, self._idx(slot), B, G)
+        fuse_logits = _HeadFn.apply(self.out_head[0], h_cls, self._idx(slot), B, G, self.grad_sync)
         return {"fuse_embeds": fuse.detach().view(B, G, D), "fuse_logits": fuse_logits}
 
     # ---------------------------------------------------------------------------------------------------
@@ -487,7 +507,7 @@ class NavModel(nn.Module):
         h_cls = self.lang_model.hidden_rows(pp, vis, pp.cls_rows)
         n_out = self.out_head[0].weight.shape[0]
         slot = np.where(np.arange(n_out)[None, :] < cand_nums[:, None], np.arange(n_out)[None, :], -1)   # [i, cand_nums:] = -inf
-        preds = _HeadFn.apply(self.out_head[0], h_cls, self._idx(slot), B, n_out)
+        preds = _HeadFn.apply(self.out_head[0], h_cls, self._idx(slot), B, n_out, self.grad_sync)
         return {"obj_logits": preds}
 
 

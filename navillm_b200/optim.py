@@ -36,6 +36,7 @@ class FlatAdamW:
     @torch.no_grad()
     def step(self, max_grad_norm: float | None = None, write_clipped_grad: bool = False):
         lib = _lib.load()
+        self.model._settle_lazy_zero()               # a lazy zero_grad with no backward since: gradients are zero, not stale
         self.step_count += 1
         lr = self.param_groups[0]["lr"]
         state = None
@@ -77,7 +78,18 @@ class FlatAdamW:
 
     def load_state_dict(self, sd):
         ms, vs = self._named_views(self.m), self._named_views(self.v)
+        names = [n for n, p in self.model.named_parameters() if p.requires_grad]
+        idx = sd["param_groups"][0].get("params")
+        if idx is not None and len(idx) != len(ms):
+            raise ValueError(f"optimizer state covers {len(idx)} parameters, this model has {len(ms)} trainable parameters")
         for i, st in sd["state"].items():
-            ms[int(i)].copy_(st["exp_avg"]); vs[int(i)].copy_(st["exp_avg_sq"])
+            i = int(i)
+            if not 0 <= i < len(ms):
+                raise ValueError(f"optimizer state index {i} out of range (model has {len(ms)} trainable parameters)")
+            for key, dst in (("exp_avg", ms[i]), ("exp_avg_sq", vs[i])):
+                if tuple(st[key].shape) != tuple(dst.shape):
+                    raise ValueError(f"optimizer state {i} ({names[i]}): {key} has shape {tuple(st[key].shape)}, the parameter "
+                                     f"has {tuple(dst.shape)} -- was the checkpoint written for a different parameter order?")
+            ms[i].copy_(st["exp_avg"]); vs[i].copy_(st["exp_avg_sq"])
             self.step_count = int(st["step"])
         self.param_groups[0].update({k: v for k, v in sd["param_groups"][0].items() if k != "params"})

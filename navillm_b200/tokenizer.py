@@ -115,8 +115,10 @@ class HFTokenizerAdapter:
     """The reference's own construction (models/modified_lm.py:56-75) for a local tokenizer directory."""
 
     def __init__(self, path: str):
-        from transformers import AutoTokenizer
-        self.tok = AutoTokenizer.from_pretrained(path, padding_side="left", truncation_side="left")
+        # the slow sentencepiece LlamaTokenizer, like the reference (models/modified_lm.py:57): the fast tokenizer can
+        # split text around added special tokens differently from what released checkpoints were trained with
+        from transformers import LlamaTokenizer
+        self.tok = LlamaTokenizer.from_pretrained(path, padding_side="left", truncation_side="left")
         self.tok.add_special_tokens({"additional_special_tokens": list(SPECIAL_TOKENS)})
         if self.tok.pad_token is None:
             self.tok.add_special_tokens({"pad_token": "<PAD>"})

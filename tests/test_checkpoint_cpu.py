@@ -81,7 +81,11 @@ def test_feature_store_matches_hdf5_reader_semantics(tmp_path):
     assert one.shape == (16,) and np.array_equal(one, blocks["scanB"][:16].astype(np.float32))
     cached = db.get_image_feature("scanA", "vp1", load_in_memory=True)
     assert db.get_image_feature("scanA", "vp1") is cached
-    # fp16 storage (the default: 36 x 1408 blocks halve to 99 KB): values within half precision of the fp32 cast
-    FeatureStore.build(tmp_path / "h", blocks.items())
+    # the default storage dtype is float32: exactly the reference reader's cast
+    FeatureStore.build(tmp_path / "d", blocks.items())
+    d = FeatureStore(str(tmp_path / "d"), image_feat_size=16).get_image_feature("scanA", "vp2")
+    assert np.array_equal(d, blocks["scanA_vp2"][:, :16].astype(np.float32))
+    # opt-in fp16 storage (36 x 1408 blocks halve to 99 KB): values within half precision of the fp32 cast
+    FeatureStore.build(tmp_path / "h", blocks.items(), dtype="float16")
     h = FeatureStore(str(tmp_path / "h"), image_feat_size=16).get_image_feature("scanA", "vp2")
     assert np.allclose(h, blocks["scanA_vp2"][:, :16], atol=2e-3, rtol=1e-3)

@@ -118,6 +118,39 @@ def test_navmodel_all_modes_match_reference(cuda_dev, pano_precision):
         check("qa grad " + name, named[name].grad, gr, t["qa_grads"][name], k=3.0, floor=5e-2)
 
 
+def test_lang_model_forward_direct(cuda_dev):
+    """ModifiedLlamaForCausalLM.forward called the way a reference caller would (models/modified_lm.py:89-146): loss,
+    [B,S,D] hidden states and (on request) [B,S,V] logits with the special tokens at -inf, against the oracle."""
+    from oracle import navillm_oracle as O
+    from tests.test_oracle_golden import load
+    g, cfg, tok = load("amp_bf16")
+    _, cfg32, _ = load("fp32")
+    model, _ = build_model(g, cuda_dev)
+    sd = g["state_dict"]
+    sd32 = {k: v.float() for k, v in sd.items()}
+    text = tok([["Question : what <cand> <cand> is <hist> this", "a red chair </s>"], ["Describe <cand> <hist> <hist>", "kitchen </s>"]])
+    ids, mask = text["input_ids"], text["attention_mask"]
+    labels = ids.clone()
+    labels[text["token_type_ids"] == 0] = -100
+    n_c, n_h = int((ids == tok.special["<cand>"]).sum()), int((ids == tok.special["<hist>"]).sum())
+    gen = torch.Generator().manual_seed(3)
+    cand, hist = torch.randn(n_c, cfg.hidden, generator=gen), torch.randn(n_h, cfg.hidden, generator=gen)
+    ref = O.modified_lm_forward(sd, cfg, ids, mask, labels=labels, cand_vis=cand, hist_vis=hist)
+    truth = O.modified_lm_forward(sd32, cfg32, ids, mask, labels=labels, cand_vis=cand, hist_vis=hist)
+    out = model.lang_model(input_ids=ids, attention_mask=mask, labels=labels, cand_vis=cand.to(cuda_dev), hist_vis=hist.to(cuda_dev),
+                           return_logits=True, use_cache=False, output_hidden_states=True)
+    m = mask.bool()
+    check("lm loss", out.loss.detach(), ref["loss"].detach(), truth["loss"].detach())
+    check("hidden_states", out.hidden_states.detach()[m.to(cuda_dev)], ref["hidden_states"].detach()[m], truth["hidden_states"].detach()[m])
+    check("logits", out["logits"].detach()[m.to(cuda_dev)], ref["logits"].detach()[m], truth["logits"].detach()[m])
+    assert out.hidden_states.shape == ref["hidden_states"].shape and out.logits.shape == ref["logits"].shape
+    assert float(out.hidden_states[~m.to(cuda_dev)].abs().sum()) == 0.0            # pad rows: documented zeros
+    plain = model.lang_model(input_ids=ids, attention_mask=mask, cand_vis=cand.to(cuda_dev), hist_vis=hist.to(cuda_dev))
+    assert plain.loss is None and plain.logits is None and plain.hidden_states.shape == ref["hidden_states"].shape
+    with pytest.raises(NotImplementedError):
+        model.lang_model(input_ids=ids[:, -1:], attention_mask=mask, past_key_values=[(None, None)])
+
+
 def test_wrong_mode_and_cpu_fail_loudly(cuda_dev):
     g = torch.load(GOLD / "nav_amp_bf16.pt", weights_only=False)
     model, tok = build_model(g, cuda_dev)
