@@ -35,6 +35,12 @@ extern "C" {
 /* ---- runtime ---------------------------------------------------------------------------------------- */
 const char* nv_last_error(void);
 int nv_abi_version(void);
+/* Programmatic dependent launch for the decode chain (generate(): HF GenerationMixin greedy loop reached from
+ * models/nav_model.py:324-338,388-399): when on, nv_embed_fwd / nv_rmsnorm_fwd / nv_gemm_skinny[_swiglu]_bf16 /
+ * nv_decode_rope_kv / nv_decode_attn / nv_add_int / nv_argmax_masked are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization so a kernel's prologue (and the skinny GEMM's first weight tiles)
+ * overlaps the tail of its predecessor.  Returns the previous setting.  Process-wide; default off. */
+int nv_set_pdl(int on);
 int nv_device_check(void); /* NV_OK iff the current device is sm_100-class */
 int nv_sm_count(void);
 
@@ -88,7 +94,7 @@ int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ldk, const vo
                 void* dk, int64_t lddk, void* dv, int64_t lddv, const int* cu_seqlens, int B, int T, int H, int head_dim,
                 int total_blocks, float scale, const int* rope_pos, const void* cos_t, const void* sin_t, void* stream);
 /* Developer hook (no reference counterpart): per-CTA SM-clock phase trace of the last nv_attn_bwd (kernel 0 = dk/dv
- * pass, 1 = dq pass).  Returns the number of 64-bit words copied, 0 unless built with -DNV_ATTN_TRACE
+ * pass, 1 = dq pass) or nv_attn_fwd (kernel 2).  Returns the number of 64-bit words copied, 0 unless built with -DNV_ATTN_TRACE
  * (tools/attn_trace.py). */
 int nv_debug_attn_trace(int kernel, unsigned long long* out, int max_words);
 

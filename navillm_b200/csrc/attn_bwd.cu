@@ -598,6 +598,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
 // Developer hook: copy the phase trace of the last nv_attn_bwd (kernel 0 = dk/dv pass, 1 = dq pass) to the host.
 // Returns the number of 64-bit words written, 0 when the library was built without -DNV_ATTN_TRACE.
 extern "C" int nv_debug_attn_trace(int kernel, unsigned long long* out, int max_words) {
+  if (kernel == 2 && out) return nv::attn_fwd_trace_copy(out, max_words);      // forward kernel (attn_fwd.cu)
 #ifdef NV_ATTN_TRACE
   if (kernel < 0 || kernel > 1 || !out) return 0;
   const int n = max_words < 256 * 64 ? max_words : 256 * 64;

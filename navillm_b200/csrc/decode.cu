@@ -56,6 +56,8 @@ __global__ void kv_append_kernel(const __nv_bfloat16* __restrict__ qkv, int64_t 
 __global__ void decode_rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int64_t ld, const int* __restrict__ lens,
                                       const __nv_bfloat16* __restrict__ cos_t, const __nv_bfloat16* __restrict__ sin_t,
                                       __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc, int B, int Smax, int H) {
+  griddep_launch();
+  griddep_wait();
   const int HD = H * 128;
   const int n_rot = B * 2 * H * 8, n_v = B * (HD >> 3);
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n_rot + n_v; idx += gridDim.x * blockDim.x) {
@@ -100,14 +102,18 @@ __global__ void decode_rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int64_t l
 }
 
 // One new query per sequence over its cache (keys 0..lens[b], the new token included: call after append).
-// CTA = (b, h), 4 warps; half-warps stream keys with 16-byte loads; per-warp online softmax, merged in smem.
-__global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
+// CTA = (b, h), DA_WARPS warps; half-warps stream keys with 16-byte loads; per-warp online softmax, merged in smem.
+// (8 warps: 256 (b, h) CTAs of 4 warps kept too few loads in flight for a 50 MB cache read; all CTAs are co-resident.)
+constexpr int DA_WARPS = 8;
+__global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
                                                           const __nv_bfloat16* __restrict__ kc,
                                                           const __nv_bfloat16* __restrict__ vc,
                                                           const int* __restrict__ lens, __nv_bfloat16* __restrict__ out,
                                                           int64_t ldo, int Smax, int H, float scale) {
-  __shared__ float s_m[4], s_l[4];
-  __shared__ float s_acc[4][128];
+  __shared__ float s_m[DA_WARPS], s_l[DA_WARPS];
+  __shared__ float s_acc[DA_WARPS][128];
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.x / H, h = blockIdx.x % H;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, hl = lane & 15;          // half-warp id, lane within the half (8 dims each)
@@ -121,20 +127,29 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* _
   // before the first use, which is what a latency-bound streaming loop needs (one key per half-warp and
   // iteration kept ~1 MB in flight chip-wide and ran at 35 us for 52 MB of cache).
   constexpr int KPI = 4;
-  for (int j0 = w * 2 * KPI; j0 < n; j0 += 8 * KPI) {
-    const int jb = j0 + half * KPI;
-    uint4 kraw[KPI], vraw[KPI];
+  auto load_keys = [&](int jb, uint4 (&kr)[KPI], uint4 (&vr)[KPI]) {
 #pragma unroll
     for (int u = 0; u < KPI; ++u) {
       if (jb + u < n) {
         const int64_t off = ((int64_t)b * Smax + jb + u) * HD + h * 128 + hl * 8;
-        kraw[u] = *reinterpret_cast<const uint4*>(kc + off);
-        vraw[u] = *reinterpret_cast<const uint4*>(vc + off);
+        kr[u] = *reinterpret_cast<const uint4*>(kc + off);
+        vr[u] = *reinterpret_cast<const uint4*>(vc + off);
       } else {
-        kraw[u] = make_uint4(0, 0, 0, 0);
-        vraw[u] = make_uint4(0, 0, 0, 0);
+        kr[u] = make_uint4(0, 0, 0, 0);
+        vr[u] = make_uint4(0, 0, 0, 0);
       }
     }
+  };
+  // software pipeline: the loads of the NEXT 8 keys are in flight while the current ones are reduced (the loop is a chain
+  // of DRAM-latency-long iterations otherwise)
+  uint4 knext[KPI], vnext[KPI];
+  load_keys(w * 2 * KPI + half * KPI, knext, vnext);
+  for (int j0 = w * 2 * KPI; j0 < n; j0 += DA_WARPS * 2 * KPI) {
+    const int jb = j0 + half * KPI;
+    uint4 kraw[KPI], vraw[KPI];
+#pragma unroll
+    for (int u = 0; u < KPI; ++u) { kraw[u] = knext[u]; vraw[u] = vnext[u]; }
+    if (j0 + DA_WARPS * 2 * KPI < n) load_keys(jb + DA_WARPS * 2 * KPI, knext, vnext);
     float sc[KPI];
 #pragma unroll
     for (int u = 0; u < KPI; ++u) {
@@ -193,10 +208,12 @@ __global__ void __launch_bounds__(128) decode_attn_kernel(const __nv_bfloat16* _
   __syncthreads();
   if (threadIdx.x < 128) {
     const int d = threadIdx.x;
-    float mm = fmaxf(fmaxf(s_m[0], s_m[1]), fmaxf(s_m[2], s_m[3]));
+    float mm = s_m[0];
+#pragma unroll
+    for (int k = 1; k < DA_WARPS; ++k) mm = fmaxf(mm, s_m[k]);
     float num = 0.f, den = 0.f;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < DA_WARPS; ++k) {
       const float a = (s_m[k] == -INFINITY) ? 0.f : exp2f((s_m[k] - mm) * sl2);
       num += s_acc[k][d] * a;
       den += s_l[k] * a;
@@ -214,6 +231,8 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const __nv_bfloat16* __res
   __shared__ float sv[32];
   __shared__ int si[32];
   __shared__ int s_special[64];
+  griddep_launch();
+  griddep_wait();
   const int b = blockIdx.x;
   const int ns = min(n_special, 64);
   if (threadIdx.x < ns) s_special[threadIdx.x] = special[threadIdx.x];
@@ -270,6 +289,8 @@ __global__ void __launch_bounds__(1024) argmax_kernel(const __nv_bfloat16* __res
 }
 
 __global__ void add_int_kernel(int* __restrict__ x, int n, int delta) {
+  griddep_launch();
+  griddep_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] += delta;
 }
@@ -323,9 +344,8 @@ int nv_decode_rope_kv(void* qkv, int64_t ld, const int* lens, const void* cos_t,
   NV_REQUIRE(head_dim == 128 && (ld & 7) == 0, "nv_decode_rope_kv: head_dim must be 128, ld %% 8 == 0");
   if (B == 0) return NV_OK;
   const int work = B * 2 * H * 8 + B * (H * 128 / 8);
-  decode_rope_kv_kernel<<<(work + 255) / 256, 256, 0, S_(stream)>>>(BF(qkv), ld, lens, CBF(cos_t), CBF(sin_t), BF(kcache),
-                                                                    BF(vcache), B, Smax, H);
-  NV_LAUNCH_CHECK();
+  NV_CUDA(launch_pdl(decode_rope_kv_kernel, dim3((work + 255) / 256), dim3(256), 0, S_(stream), BF(qkv), ld, lens, CBF(cos_t),
+                     CBF(sin_t), BF(kcache), BF(vcache), B, Smax, H));
   return NV_OK;
 }
 
@@ -333,23 +353,22 @@ int nv_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* v
                    int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream) {
   NV_REQUIRE(head_dim == 128, "nv_decode_attn: head_dim must be 128");
   if (B == 0) return NV_OK;
-  decode_attn_kernel<<<B * H, 128, 0, S_(stream)>>>(CBF(q), ldq, CBF(kcache), CBF(vcache), lens, BF(out), ldo, Smax, H, scale);
-  NV_LAUNCH_CHECK();
+  NV_CUDA(launch_pdl(decode_attn_kernel, dim3(B * H), dim3(DA_WARPS * 32), 0, S_(stream), CBF(q), ldq, CBF(kcache), CBF(vcache), lens, BF(out), ldo,
+                     Smax, H, scale));
   return NV_OK;
 }
 
 int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id,
                      int pad_id, int stop_on_eos, int* next, int B, void* stream) {
   if (B == 0) return NV_OK;
-  argmax_kernel<<<B, 1024, 0, S_(stream)>>>(CBF(logits), ld, V, special, n_special, finished, eos_id, pad_id, stop_on_eos, next);
-  NV_LAUNCH_CHECK();
+  NV_CUDA(launch_pdl(argmax_kernel, dim3(B), dim3(1024), 0, S_(stream), CBF(logits), ld, V, special, n_special, finished, eos_id, pad_id,
+                     stop_on_eos, next));
   return NV_OK;
 }
 
 int nv_add_int(int* x, int n, int delta, void* stream) {
   if (n == 0) return NV_OK;
-  add_int_kernel<<<(n + 255) / 256, 256, 0, S_(stream)>>>(x, n, delta);
-  NV_LAUNCH_CHECK();
+  NV_CUDA(launch_pdl(add_int_kernel, dim3((n + 255) / 256), dim3(256), 0, S_(stream), x, n, delta));
   return NV_OK;
 }
 

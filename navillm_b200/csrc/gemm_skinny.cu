@@ -86,20 +86,42 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  griddep_launch();                                        // the next kernel of the stream may start its own prologue
   if (warp == 0) {
     const int32_t n0 = swiglu_f ? n_blk * 64 : n_blk * SK_BN;
-    for (uint32_t i = 0; i < nkb; ++i) {
+    auto load_w = [&](uint32_t stage, int32_t k0) {
+      if (swiglu_f) {                                                                   // box {64 k, 64 n}: gate half, up half
+        tma_load_2d(smem_w + stage * SK_W_BYTES, &tmap_w, &full_bar[stage], k0, n0);
+        tma_load_2d(smem_w + stage * SK_W_BYTES + SK_W_BYTES / 2, &tmap_w, &full_bar[stage], k0, (int32_t)swiglu_f + n0);
+      } else {
+        tma_load_2d(smem_w + stage * SK_W_BYTES, &tmap_w, &full_bar[stage], k0, n0);   // box {64 k, 128 n}
+      }
+    };
+    // Programmatic dependent launch: the WEIGHTS do not depend on the previous kernel of the stream, so the first ring of
+    // weight tiles is requested before waiting for it (weight streaming continues across the kernel boundary); the
+    // activations X are its output and are loaded after the wait.
+    const uint32_t pre = min(nkb, SK_STAGES);
+    if (elect_one()) {
+      for (uint32_t i = 0; i < pre; ++i) {
+        mbar_arrive_expect_tx(&full_bar[i], SK_STAGE_BYTES);
+        load_w(i, (kb0 + i) * SK_BK);
+      }
+    }
+    __syncwarp();
+    griddep_wait();
+    if (elect_one()) {
+      for (uint32_t i = 0; i < pre; ++i)
+        tma_load_2d(smem_x + i * SK_X_BYTES, &tmap_x, &full_bar[i], (kb0 + i) * SK_BK, 0);   // box {64 k, 16 m} (rows >= M: zeros)
+    }
+    __syncwarp();
+    for (uint32_t i = pre; i < nkb; ++i) {
       const uint32_t stage = i % SK_STAGES, phase = (i / SK_STAGES) & 1;
       mbar_wait(&empty_bar[stage], phase ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&full_bar[stage], SK_STAGE_BYTES);
         const int32_t k0 = (kb0 + i) * SK_BK;
-        if (swiglu_f) {                                                                 // box {64 k, 64 n}: gate half, up half
-          tma_load_2d(smem_w + stage * SK_W_BYTES, &tmap_w, &full_bar[stage], k0, n0);
-          tma_load_2d(smem_w + stage * SK_W_BYTES + SK_W_BYTES / 2, &tmap_w, &full_bar[stage], k0, (int32_t)swiglu_f + n0);
-        } else
-        tma_load_2d(smem_w + stage * SK_W_BYTES, &tmap_w, &full_bar[stage], k0, n0);   // box {64 k, 128 n}
-        tma_load_2d(smem_x + stage * SK_X_BYTES, &tmap_x, &full_bar[stage], k0, 0);    // box {64 k, 16 m} (rows >= M: zeros)
+        load_w(stage, k0);
+        tma_load_2d(smem_x + stage * SK_X_BYTES, &tmap_x, &full_bar[stage], k0, 0);
       }
       __syncwarp();
     }
@@ -127,6 +149,7 @@ gemm_skinny_tcgen05(const __grid_constant__ CUtensorMap tmap_w, const __grid_con
   const uint32_t quarter = warp & 3;
   const uint32_t nl = quarter * 32 + lane;               // weight row inside the tile (epilogue warps only)
   if (warp >= 2) {
+    griddep_wait();                                        // before the first read of `addend` / write of C
     if (nkb > 0) {
       mbar_wait(acc_full, 0);
       tc_fence_after();
@@ -219,13 +242,18 @@ static int skinny_launch(const void* X, int64_t ldx, const void* W, int64_t ldw,
   cfg.blockDim = dim3(SK_THREADS);
   cfg.dynamicSmemBytes = SK_DYN_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = splits;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (g_pdl) {                                             // see griddep_wait() in the kernel
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   NV_CUDA(cudaLaunchKernelEx(&cfg, gemm_skinny_tcgen05, tw, tx, reinterpret_cast<__nv_bfloat16*>(C), ldc,
                              reinterpret_cast<const __nv_bfloat16*>(addend), ld_add, (uint32_t)M, (uint32_t)N, (uint32_t)K,
                              splits, swiglu_f));

@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(RMS_THREADS) rmsnorm_fwd_kernel(const __nv_bfl
                                                                   __nv_bfloat16* __restrict__ y, int64_t ldy,
                                                                   float* __restrict__ rstd_out, int D, float eps) {
   __shared__ float red[33];
+  griddep_launch();
+  griddep_wait();
   const int row = blockIdx.x;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (int64_t)row * ldx);
   const uint4* wr = reinterpret_cast<const uint4*>(w);
@@ -293,6 +295,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, int64_t 
 __global__ void embed_fwd_kernel(const int* __restrict__ ids, const __nv_bfloat16* __restrict__ E, int V,
                                  const int* __restrict__ vis_src, const float* __restrict__ vis,
                                  __nv_bfloat16* __restrict__ out, int T, int D) {
+  griddep_launch();
+  griddep_wait();
   const int vecs = D >> 3;
   const int64_t total = (int64_t)T * vecs;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -531,8 +535,7 @@ int nv_rmsnorm_fwd(const void* x, int64_t ldx, const void* w, void* y, int64_t l
   NV_REQUIRE(T >= 0 && D > 0 && (D & 7) == 0 && D <= 8 * RMS_MAX_VEC * RMS_THREADS, "nv_rmsnorm_fwd: bad D=%d", D);
   NV_REQUIRE((ldx & 7) == 0 && (ldy & 7) == 0, "nv_rmsnorm_fwd: leading dims must be multiples of 8");
   if (T == 0) return NV_OK;
-  rmsnorm_fwd_kernel<<<T, RMS_THREADS, 0, S_(stream)>>>(CBF(x), ldx, CBF(w), BF(y), ldy, rstd, D, eps);
-  NV_LAUNCH_CHECK();
+  NV_CUDA(launch_pdl(rmsnorm_fwd_kernel, dim3(T), dim3(RMS_THREADS), 0, S_(stream), CBF(x), ldx, CBF(w), BF(y), ldy, rstd, D, eps));
   return NV_OK;
 }
 
@@ -588,8 +591,7 @@ int nv_embed_fwd(const int* ids, const void* E, int V, const int* vis_src, const
                  void* stream) {
   NV_REQUIRE((D & 7) == 0, "nv_embed_fwd: D %% 8");
   if (T == 0) return NV_OK;
-  embed_fwd_kernel<<<grid_for((int64_t)T * (D >> 3), 256), 256, 0, S_(stream)>>>(ids, CBF(E), V, vis_src, vis, BF(out), T, D);
-  NV_LAUNCH_CHECK();
+  NV_CUDA(launch_pdl(embed_fwd_kernel, dim3(grid_for((int64_t)T * (D >> 3), 256)), dim3(256), 0, S_(stream), ids, CBF(E), V, vis_src, vis, BF(out), T, D));
   return NV_OK;
 }
 

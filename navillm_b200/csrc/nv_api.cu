@@ -27,6 +27,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
   return (int)e;
 }
 
+int g_pdl = 0;
+
 int sm_count() {
   static int n = -1;
   if (n < 0) {
@@ -95,6 +97,12 @@ extern "C" {
 const char* nv_last_error(void) { return nv::g_err; }
 
 int nv_abi_version(void) { return 1; }
+
+int nv_set_pdl(int on) {
+  const int prev = nv::g_pdl;
+  nv::g_pdl = on ? 1 : 0;
+  return prev;
+}
 
 // 0 when an sm_100-class device is current, NV_ERR_NO_DEVICE otherwise.
 int nv_device_check(void) {

@@ -106,6 +106,16 @@ class LlamaModelParams(nn.Module):
         self.layers = nn.ModuleList([_Layer(d, dtype) for _ in range(d.n_layers)])
         self.norm = _Norm(d.hidden, dtype)
 
+    def flat_order(self) -> List[nn.Parameter]:
+        """Parameter order of the flat buffer: q|k|v and gate|up of a layer adjacent (fused [3D,D] / [2F,D] views).  NOT
+        ``parameters()`` order, which follows the reference's registration order (see ``_MLP``)."""
+        ps: List[nn.Parameter] = []
+        for lyr in self.layers:
+            a, m = lyr.self_attn, lyr.mlp
+            ps += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.o_proj.weight, m.gate_proj.weight, m.up_proj.weight,
+                   m.down_proj.weight, lyr.input_layernorm.weight, lyr.post_attention_layernorm.weight]
+        return ps + [self.embed_tokens.weight, self.norm.weight]
+
 
 def init_llama_params_(model: LlamaModelParams, lm_head: _Linear, std: float = 0.02, seed: int = 0) -> None:
     """HF default init (normal(0, 0.02) for linears/embeddings, ones for RMSNorm), generated on the host."""
@@ -160,22 +170,30 @@ class FlatParams:
         for p, o in zip(self.params, self.offsets):
             p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
 
-    def view(self, first: nn.Parameter, n_params: int, shape) -> torch.Tensor:
-        i = next(k for k, p in enumerate(self.params) if p is first)
+    def _fused_span(self, members, shape):
+        """Offset / size of the fused view over ``members`` (parameters that must sit back to back, in this order, in the
+        flat buffer -- identity-checked: a look-alike neighbour of the same size must not pass)."""
+        i = next(k for k, p in enumerate(self.params) if p is members[0])
         o = self.offsets[i]
         numel = 1
         for s in shape:
             numel *= s
-        # adjacency holds only if the fused members are unpadded multiples of the alignment
-        assert self.offsets[i + n_params - 1] + self.params[i + n_params - 1].numel() - o == numel, "fused view not contiguous"
+        end = o
+        for j, m in enumerate(members):
+            if i + j >= len(self.params) or self.params[i + j] is not m or self.offsets[i + j] != end:
+                raise RuntimeError("fused weight view: the members are not adjacent, in order and unpadded in the flat buffer "
+                                   "(build FlatParams from LlamaModelParams.flat_order())")
+            end += m.numel()
+        if end - o != numel:
+            raise RuntimeError(f"fused weight view: members hold {end - o} elements, shape {tuple(shape)} needs {numel}")
+        return o, numel
+
+    def view(self, members, shape) -> torch.Tensor:
+        o, numel = self._fused_span(members, shape)
         return self.flat[o:o + numel].view(shape)
 
-    def grad_view(self, first: nn.Parameter, n_params: int, shape) -> torch.Tensor:
-        i = next(k for k, p in enumerate(self.params) if p is first)
-        o = self.offsets[i]
-        numel = 1
-        for s in shape:
-            numel *= s
+    def grad_view(self, members, shape) -> torch.Tensor:
+        o, numel = self._fused_span(members, shape)
         return self.flat_grad[o:o + numel].view(shape)
 
 
@@ -224,12 +242,14 @@ class LlamaCore:
         self.wqkv, self.gqkv, self.wo, self.go, self.wgu, self.ggu, self.wd, self.gd = [], [], [], [], [], [], [], []
         for lyr in model.layers:
             a, m = lyr.self_attn, lyr.mlp
-            self.wqkv.append(flat.view(a.q_proj.weight, 3, (3 * D, D)))
-            self.gqkv.append(flat.grad_view(a.q_proj.weight, 3, (3 * D, D)))
+            qkv = [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight]
+            self.wqkv.append(flat.view(qkv, (3 * D, D)))
+            self.gqkv.append(flat.grad_view(qkv, (3 * D, D)))
             self.wo.append(a.o_proj.weight.data)
             self.go.append(a.o_proj.weight.grad)
-            self.wgu.append(flat.view(m.gate_proj.weight, 2, (2 * F, D)))
-            self.ggu.append(flat.grad_view(m.gate_proj.weight, 2, (2 * F, D)))
+            gu = [m.gate_proj.weight, m.up_proj.weight]
+            self.wgu.append(flat.view(gu, (2 * F, D)))
+            self.ggu.append(flat.grad_view(gu, (2 * F, D)))
             self.wd.append(m.down_proj.weight.data)
             self.gd.append(m.down_proj.weight.grad)
         self.cos, self.sin = rope_tables(dims, flat.flat.device)

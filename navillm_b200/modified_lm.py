@@ -14,6 +14,8 @@ reference holds values computed from pad embeddings that nothing reads.
 """
 from __future__ import annotations
 
+import collections
+import os
 from types import SimpleNamespace
 from typing import List, Optional
 
@@ -319,13 +321,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
 
     # ---- device materialisation ----
     def lm_parameters(self) -> List[nn.Parameter]:
-        ps: List[nn.Parameter] = []
-        for lyr in self.model.layers:
-            a, m = lyr.self_attn, lyr.mlp
-            ps += [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight, a.o_proj.weight, m.gate_proj.weight, m.up_proj.weight,
-                   m.down_proj.weight, lyr.input_layernorm.weight, lyr.post_attention_layernorm.weight]
-        ps += [self.model.embed_tokens.weight, self.model.norm.weight, self.lm_head.weight]
-        return ps
+        return self.model.flat_order() + [self.lm_head.weight]
 
     def materialize(self, device: torch.device, extra_params: Optional[List[nn.Parameter]] = None) -> FlatParams:
         """Move the LM parameters into one flat bf16 buffer on ``device`` (+ ``extra_params``: the bf16 heads of
@@ -335,6 +331,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
         if extra_params is not None:
             self._extra_params = list(extra_params)
         params = self.lm_parameters() + list(getattr(self, "_extra_params", []))
+        self.__dict__.pop("_decode_states", None)     # captured decode graphs hold pointers into the old buffers
         self.flat = FlatParams(params, device)
         self.core = LlamaCore(self.dims, self.model, self.flat)
         self.special_ids_dev = torch.tensor(self.special_token_ids, dtype=torch.int32, device=device)
@@ -464,6 +461,35 @@ class ModifiedLlamaForCausalLM(nn.Module):
 
 
     # ---- generation (models/nav_model.py:324-338,388-399; HF GenerationMixin greedy / sampling) ----
+    decode_pdl = os.environ.get("NAVILLM_DECODE_PDL", "1") != "0"   # developer knob: 0 = plain stream-ordered launches
+    max_decode_states = 2        # cached (KV buffers + captured decode graph) sets, least recently used evicted
+
+    def _decode_state(self, B: int, Smax: int, key_extra: tuple, want_graph: bool):
+        """Persistent per-shape decode state: the contiguous KV cache [B, Smax, D] per layer, the step's I/O buffers and --
+        once captured -- the CUDA graph of ONE greedy decode step.  Capturing and instantiating the ~260-node graph costs
+        more than the 127 replays of a C3 generation save, so it is done once per (batch, cache length, stop rule) and
+        reused by every later ``generate`` call (evaluation loops call generate with the same shapes over and over)."""
+        states = self.__dict__.setdefault("_decode_states", collections.OrderedDict())
+        key = (B, Smax) + key_extra
+        st = states.get(key) if want_graph else None
+        if st is not None:
+            states.move_to_end(key)
+            return st
+        dev, d = self._device(), self.dims
+        V = self.lm_head.weight.shape[0]
+        st = SimpleNamespace(
+            kc=[torch.empty((B, Smax, d.hidden), dtype=bf16, device=dev) for _ in range(d.n_layers)],
+            vc=[torch.empty((B, Smax, d.hidden), dtype=bf16, device=dev) for _ in range(d.n_layers)],
+            logits=torch.empty((B, (V + 63) // 64 * 64), dtype=bf16, device=dev)[:, :V],
+            next_ids=torch.empty((B,), dtype=torch.int32, device=dev),
+            finished=torch.zeros((B,), dtype=torch.int32, device=dev),
+            lens=torch.zeros((B,), dtype=torch.int32, device=dev), graph=None)
+        if want_graph:
+            states[key] = st
+            while len(states) > self.max_decode_states:
+                states.popitem(last=False)
+        return st
+
     @torch.no_grad()
     def generate(self, input_ids, attention_mask, cand_vis=None, hist_vis=None, obj_vis=None, max_new_tokens: int = 20,
                  do_sample: bool = False, temperature: float = 1.0, eos_token_id: Optional[int] = None,
@@ -471,8 +497,9 @@ class ModifiedLlamaForCausalLM(nn.Module):
                  stop_on_eos: bool = True, use_cuda_graph: bool = True, stats: Optional[dict] = None, **unused) -> torch.Tensor:
         """Prefill on the packed kernels (positions = cumsum(mask)-1 like HF generate; visual tokens injected only
         here, as in models/modified_lm.py:195-197), then one token per step over a pre-allocated KV cache.  The
-        greedy step has static shapes and is replayed as a CUDA graph.  Returns [B, S0 + n_new] int64 ids (prompt
-        part copied from the input; finished rows continue with pad_token_id like HF greedy search)."""
+        greedy step has static shapes and is replayed as a CUDA graph (captured once per shape, see ``_decode_state``).
+        Returns [B, S0 + n_new] int64 ids (prompt part copied from the input; finished rows continue with pad_token_id
+        like HF greedy search)."""
         self._ensure()
         dev = self._device()
         core, d = self.core, self.dims
@@ -480,14 +507,18 @@ class ModifiedLlamaForCausalLM(nn.Module):
         pad = self.tokenizer.unk_token_id if pad_token_id is None else pad_token_id
         ev = None
         if stats is not None:                                     # bench.py: device-side phase times (forces one sync at the end)
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
             ev[0].record()
         pp = PackedPrompt(input_ids, attention_mask, self, dev, generate_positions=True)
         vis = self.cat_vis(cand_vis, hist_vis, obj_vis, pp)
-        B, H, D = pp.B, d.n_heads, d.hidden
-        Smax = (max(pp.seqlens) + max_new_tokens + 63) // 64 * 64
-        kc = [torch.empty((B, Smax, D), dtype=bf16, device=dev) for _ in range(d.n_layers)]
-        vc = [torch.empty((B, Smax, D), dtype=bf16, device=dev) for _ in range(d.n_layers)]
+        B = pp.B
+        greedy = (not do_sample) and trie is None and not logits_processor
+        graphed = greedy and use_cuda_graph
+        Smax = (max(pp.seqlens) + max_new_tokens + 127) // 128 * 128          # bucketed: more reuse of the cached state
+        st = self._decode_state(B, Smax, (int(eos), int(pad), bool(stop_on_eos)), graphed)
+        kc, vc, logits, next_ids, finished, lens = st.kc, st.vc, st.logits, st.next_ids, st.finished, st.lens
+        finished.zero_()
+        lens.copy_(torch.tensor(pp.seqlens, dtype=torch.int32), non_blocking=True)
 
         def sink(l, qkv):
             ops.kv_store_prefill(qkv, pp.cu, kc[l], vc[l], B, pp.T)
@@ -495,14 +526,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
         E = self.model.embed_tokens.weight.data
         x = ops.embed_fwd(pp.ids, E, pp.vis_src if vis is not None else None, vis)
         hid_last, _ = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=False, kv_sink=sink, out_rows=pp.last_rows)
-        V = self.lm_head.weight.shape[0]
-        Vp = (V + 63) // 64 * 64
-        logits = torch.empty((B, Vp), dtype=bf16, device=dev)[:, :V]
-        next_ids = torch.empty((B,), dtype=torch.int32, device=dev)
-        finished = torch.zeros((B,), dtype=torch.int32, device=dev)
-        lens = torch.tensor(pp.seqlens, dtype=torch.int32, device=dev)
         special = self.special_ids_dev
-        greedy = (not do_sample) and trie is None and not logits_processor
 
         def head(h_rows):
             hn, _ = ops.rmsnorm_fwd(h_rows, self.model.norm.weight.data, d.rms_eps)
@@ -550,46 +574,48 @@ class ModifiedLlamaForCausalLM(nn.Module):
             ev[1].record()
 
         def step():
-            xt = ops.embed_fwd(next_ids, E)
-            h = core.decode_step(xt, lens, kc, vc)
-            head(h)
-            ops.add_int_(lens, 1)
+            with ops.pdl(self.decode_pdl):          # programmatic dependent launch along the whole decode chain
+                xt = ops.embed_fwd(next_ids, E)
+                h = core.decode_step(xt, lens, kc, vc)
+                head(h)
+                ops.add_int_(lens, 1)
+                if greedy:
+                    ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)
 
         # HF stops when every sequence has finished.  Asking the device after EVERY token would serialise host and device
         # (one blocking read per token); finished rows only emit pad tokens, so the greedy loop looks every `check_every`
         # tokens and the surplus pad columns are trimmed below -- same ids as a per-token check.
         check_every = 8 if greedy else 1
-        graph, replays = None, 0
+        replays = 0
         for it in range(1, max_new_tokens):
             if stop_on_eos and it % check_every == 0 and bool(finished.all()):
                 break
             if not greedy:
                 for bn, t in enumerate(out_tokens[-1].tolist()):
                     host_ids[bn].append(t)
-            if greedy and use_cuda_graph:
-                if graph is None:
-                    step(); ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)   # warm-up (eager)
+            if graphed:
+                if st.graph is None:                              # first generation with this shape: eager step, then capture
+                    step()
                     out_tokens.append(next_ids.clone())
-                    graph = torch.cuda.CUDAGraph()
+                    g = torch.cuda.CUDAGraph()
                     torch.cuda.synchronize()
-                    with torch.cuda.graph(graph):
+                    with torch.cuda.graph(g):
                         step()
-                        ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)
-                    if ev is not None:
-                        ev[2].record()
+                    st.graph = g
                     continue
-                graph.replay()
+                st.graph.replay()
                 replays += 1
             else:
                 step()
-                pick(host_ids)
+                if not greedy:
+                    pick(host_ids)
             out_tokens.append(next_ids.clone())
         if ev is not None:
-            ev[3].record()
+            ev[2].record()
             torch.cuda.synchronize()
-            stats.update({"prefill_ms": ev[0].elapsed_time(ev[1]), "graph_replays": replays,
-                          "decode_ms": ev[2].elapsed_time(ev[3]) if (graph is not None and replays > 0) else None,
-                          "kv_rows": Smax, "prompt_lens": list(pp.seqlens)})
+            n_dec = len(out_tokens) - 1
+            stats.update({"prefill_ms": ev[0].elapsed_time(ev[1]), "decode_ms": ev[1].elapsed_time(ev[2]) if n_dec else None,
+                          "decode_steps": n_dec, "graph_replays": replays, "kv_rows": Smax, "prompt_lens": list(pp.seqlens)})
         new = torch.stack(out_tokens, dim=1).to(torch.int64)
         if stop_on_eos and greedy and new.shape[1] > 1:
             # trim the columns generated after the step at which the last row emitted EOS (see check_every above)

@@ -525,6 +525,20 @@ def argmax_masked(logits, special, finished, eos_id, pad_id, stop_on_eos, next_i
     return next_ids
 
 
+class pdl:
+    """Context: launch the decode-chain kernels with programmatic dependent launch (nv_set_pdl)."""
+
+    def __init__(self, on: bool = True):
+        self.on = on
+
+    def __enter__(self):
+        self.prev = _lib.load().nv_set_pdl(i32(1 if self.on else 0))
+        return self
+
+    def __exit__(self, *a):
+        _lib.load().nv_set_pdl(i32(self.prev))
+
+
 def add_int_(x, delta):
     check(_lib.load().nv_add_int(ptr(x), i32(x.numel()), i32(delta), stream_ptr()), "nv_add_int")
     return x

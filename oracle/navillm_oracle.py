@@ -325,7 +325,7 @@ def _lm_labels(text):
 
 
 def forward_summarization(sd: SD, cfg: OracleConfig, batch, tokenize, eos_token: str, training=True, max_new_tokens=50,
-                          trie=None, eos_token_id=2, pad_token_id=0):
+                          trie=None, eos_token_id=2, pad_token_id=0, return_logits=False):
     """NavModel.forward_summarization (models/nav_model.py:251-343), training branch and greedy branch."""
     vp = batch["vp_img_embeds"][:, 1:, :]                                                      # remove stop :267-268
     nav_masks = batch["vp_nav_masks"][:, 1:]
@@ -347,8 +347,11 @@ def forward_summarization(sd: SD, cfg: OracleConfig, batch, tokenize, eos_token:
     procs = [TrieLogitsProcessor(trie)] if trie is not None else []              # models/nav_model.py:321-322
     ids = greedy_generate(sd, cfg, text["input_ids"], text["attention_mask"], cand_vis=vp[nav_masks],
                           hist_vis=hist_vis_input, max_new_tokens=max_new_tokens, eos_token_id=eos_token_id,
-                          pad_token_id=pad_token_id, logits_processor=procs)
-    return {"generated_ids": ids[:, text["input_ids"].shape[1]:]}
+                          pad_token_id=pad_token_id, logits_processor=procs, return_logits=return_logits)
+    step_logits = None
+    if return_logits:
+        ids, step_logits = ids
+    return {"generated_ids": ids[:, text["input_ids"].shape[1]:], "step_logits": step_logits}
 
 
 def forward_3dqa(sd: SD, cfg: OracleConfig, batch, tokenize, eos_token: str, training=True, max_new_tokens=20):

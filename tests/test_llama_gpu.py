@@ -31,7 +31,7 @@ def build(cuda_dev, hidden=256, heads=2, inter=256, layers=2, vocab=262):
     dims = llama.LlamaDims(hidden=hidden, n_layers=layers, n_heads=heads, inter=inter, vocab=vocab)
     model = llama.LlamaModelParams(dims)
     model.load_state_dict({k[len("lang_model.model."):]: v for k, v in sd.items() if k.startswith("lang_model.model.")})
-    flat = llama.FlatParams(list(model.parameters()), cuda_dev)
+    flat = llama.FlatParams(model.flat_order(), cuda_dev)
     core = llama.LlamaCore(dims, model, flat)
     return cfg, sd, dims, model, flat, core
 

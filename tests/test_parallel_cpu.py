@@ -179,3 +179,20 @@ def test_parameter_order_matches_reference_optimizer_indexing():
                      "layers.0.self_attn.v_proj.weight", "layers.0.self_attn.o_proj.weight", "layers.0.mlp.gate_proj.weight",
                      "layers.0.mlp.down_proj.weight", "layers.0.mlp.up_proj.weight", "layers.0.input_layernorm.weight",
                      "layers.0.post_attention_layernorm.weight", "norm.weight"]
+
+
+def test_fused_views_are_identity_checked():
+    """The fused q|k|v / gate|up weight views must come from the flat-buffer order, not from parameters() order (where
+    down_proj sits between gate_proj and up_proj and has the same size as up_proj)."""
+    import pytest
+    from navillm_b200.llama import FlatParams, LlamaDims, LlamaModelParams
+    d = LlamaDims(hidden=128, n_layers=1, n_heads=1, inter=256, vocab=16)
+    m = LlamaModelParams(d)
+    mlp = m.layers[0].mlp
+    good = FlatParams(m.flat_order(), torch.device("cpu"))
+    v = good.view([mlp.gate_proj.weight, mlp.up_proj.weight], (2 * d.inter, d.hidden))
+    assert v.data_ptr() == mlp.gate_proj.weight.data_ptr() and v[d.inter:].data_ptr() == mlp.up_proj.weight.data_ptr()
+    m2 = LlamaModelParams(d)
+    bad = FlatParams(list(m2.parameters()), torch.device("cpu"))
+    with pytest.raises(RuntimeError):
+        bad.view([m2.layers[0].mlp.gate_proj.weight, m2.layers[0].mlp.up_proj.weight], (2 * d.inter, d.hidden))

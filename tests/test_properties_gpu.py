@@ -36,7 +36,7 @@ def stack(cuda_dev):
                 p.copy_(1 + 0.1 * torch.randn(p.shape, generator=g, device=cuda_dev))
             else:
                 p.normal_(0, 0.02, generator=g)
-    flat = llama.FlatParams(list(model.parameters()), cuda_dev)
+    flat = llama.FlatParams(model.flat_order(), cuda_dev)
     return dims, model, flat, llama.LlamaCore(dims, model, flat)
 
 
