@@ -491,6 +491,8 @@ def run_train(a, rank, local_rank, world, dev):
             "config": {"workload": wl["name"], "layers": a.layers, "real_tokens_per_step": tokens_real,
                        "l2": "inputs_exceed_l2 (13.5 GB of weights streamed per pass)",
                        "grad_exchange": ({"overlap": "every step, fired from the backward by navillm_b200.parallel.DistributedDataParallel; LM layer slices overlapped with the backward", "end": "every step, at the end of the backward (debug)", "none": "DISABLED (debug, invalid)"}[a.grad_sync]
+                                         + ("; transport: own in-switch all-reduce over NVLS multicast (multimem.ld_reduce / multimem.st, csrc/nvls_allreduce.cu) on a side stream"
+                                            if getattr(model, "nvls", False) else "; transport: NCCL all-reduce")
                                          + f"; {st['collectives']} collectives in {st['exchanges']} exchanges so far") if world > 1 else "n/a",
                        "zero_grad": "lazy (first wgrad of a step overwrites: beta=0)", "optimizer_step": "outside the boundary (train.py:86-89), not timed"},
             "e2e": {"value": e2e, "unit": "nav-steps/s", "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,

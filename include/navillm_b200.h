@@ -197,6 +197,15 @@ int nv_clip_coef(const float* partial, int n_partial, float max_norm, float* sta
 int nv_adamw_flat(void* p, void* g, void* m, void* v, int64_t n, int is_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, const float* clip_state, int write_clipped_grad, void* stream);
 
+/* ---- in-switch gradient all-reduce over NVLS multicast (csrc/nvls_allreduce.cu) ---------------------------------
+ * The path's one exchange step (reference: DDP's NCCL all-reduce, tools/optims.py:52-54, fired from the last backward
+ * outside no_sync, tasks/agents/mp3d_agent.py:661-667).  Elements [elem_off, elem_off + n) of a symmetric buffer whose
+ * NVLS multicast address is mc_ptr are summed across the `world` replicas in the NVSwitch (multimem.ld_reduce, fp32
+ * accumulation), scaled, and written back to every replica (multimem.st); rank r handles the r-th 1/world of the range.
+ * Call on every rank, between two cross-rank barriers.  is_bf16: 1 = bf16, 0 = fp32 elements; range 16-byte aligned. */
+int nv_multimem_allreduce(uint64_t mc_ptr, int64_t elem_off, int64_t n, int is_bf16, int rank, int world, float scale,
+                          int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,22 +143,36 @@ __device__ __forceinline__ void flush_acc_tile(const uint8_t* stage, uint32_t cw
 }
 
 // ======================================================================================================
-// dq pass
+// dq pass -- A operands in TENSOR MEMORY (tcgen05.mma ".ts" form)
 // ======================================================================================================
+// Round 1 ran this pass with every operand in shared memory and measured it smem-bandwidth-bound: 176 KB of shared-memory
+// traffic per 64-key sub-block (1375 cycles at 128 B/clk) against 768 tensor cycles, ~1550 measured (in-kernel trace).
+// Q and dO are the A operands of EVERY score MMA of the CTA, and dS is produced by the compute warps from TMEM data:
+//   * Q, dO  are written once into TMEM as bf16 (2 x 64 columns): TMA stages the two tiles in shared memory, each compute
+//            thread copies half of its own row (a row-per-thread load straight from HBM cost 5300 cycles of prologue)
+//   * dS(n)  is written with tcgen05.st straight over the S(n) columns it was computed from (no smem store, no
+//            fence.proxy.async), laid out so that every warp overwrites only columns it has already read
+// so per sub-block only the B operands (K_n, V_n: 48 KB) and the TMA fills (32 KB) touch shared memory, and the N = 64 score
+// MMAs run at their 32-cycle tensor floor instead of 48.
+//   TMEM: S[2] [0,128)  dP[2] [128,256)  dQ [256,384)  Q [384,448)  dO [448,512);  dS(n) aliases S[n & 1].
+//   smem: Q | dO staging (64 KB, once; the epilogue stages dQ there) + 5 stages of (K_n 16 KB | V_n 16 KB).  With the
+//   sub-block time down to ~800 cycles a 3-stage ring left only two sub-blocks (< the ~2000-cycle TMA latency) between a
+//   stage being freed by dQ(n) and S(n+3) needing its successor (in-kernel trace: the issuer waited for kv_full).
 struct DqSmem {
-  static constexpr uint32_t NST = 3;
-  static constexpr uint32_t Q_OFF = 0, DO_OFF = AB_T128;
+  static constexpr uint32_t NST = 5;
+  static constexpr uint32_t QDO_OFF = 0;                          // Q 32K | dO 32K
   static constexpr uint32_t KV_OFF = 2 * AB_T128;                 // NST x (K 16K | V 16K)
-  static constexpr uint32_t DS_OFF = KV_OFF + NST * 2 * AB_T64;   // 2 x 16K
-  static constexpr uint32_t BAR_OFF = DS_OFF + 2 * AB_PS;
-  // res_full, kv_full[3], kv_empty[3], sdp_full[2], sdp_empty[2], ds_full[2], ds_empty[2], done
-  static constexpr uint32_t NUM_BARS = 16;
+  static constexpr uint32_t BAR_OFF = KV_OFF + NST * 2 * AB_T64;
+  // kv_full[5], kv_empty[5], sdp_full[2], sdp_empty[2], ds_full[2], res_full, qdo_ready, done
+  static constexpr uint32_t NUM_BARS = 19;
   static constexpr uint32_t DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
+static_assert(AB_STAGE_BYTES <= 2 * AB_T128, "dQ staging reuses the Q/dO staging area");
+static_assert(DqSmem::DYN_BYTES <= 232448, "dq pass shared memory");
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
-                   const __grid_constant__ CUtensorMap tmap_v, const __grid_constant__ CUtensorMap tmap_do,
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_do,
+                   const __grid_constant__ CUtensorMap tmap_k, const __grid_constant__ CUtensorMap tmap_v,
                    const float* __restrict__ lse, const float* __restrict__ Dvec, __nv_bfloat16* __restrict__ dq,
                    int64_t lddq, const int* __restrict__ cu_seqlens, int B, int T, float scale,
                    const int* __restrict__ rope_pos, const __nv_bfloat16* __restrict__ cos_t,
@@ -166,19 +180,17 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   using L = DqSmem;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem + L::Q_OFF;
-  uint8_t* sdO = smem + L::DO_OFF;
+  uint8_t* sQdO = smem + L::QDO_OFF;
   uint8_t* sKV = smem + L::KV_OFF;
-  uint8_t* sDS = smem + L::DS_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
-  uint64_t* res_full = bars + 0;
-  uint64_t* kv_full = bars + 1;     // [3]
-  uint64_t* kv_empty = bars + 4;    // [3]
-  uint64_t* sdp_full = bars + 7;    // [2]
-  uint64_t* sdp_empty = bars + 9;   // [2]
-  uint64_t* ds_full = bars + 11;    // [2]
-  uint64_t* ds_empty = bars + 13;   // [2]
-  uint64_t* done = bars + 15;
+  uint64_t* kv_full = bars + 0;     // [5]
+  uint64_t* kv_empty = bars + 5;    // [5]
+  uint64_t* sdp_full = bars + 10;   // [2]
+  uint64_t* sdp_empty = bars + 12;  // [2]
+  uint64_t* ds_full = bars + 14;    // [2]
+  uint64_t* res_full = bars + 16;
+  uint64_t* qdo_ready = bars + 17;
+  uint64_t* done = bars + 18;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
 
   const uint32_t warp = warp_id_uniform(), lane = threadIdx.x & 31;
@@ -197,13 +209,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   }
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
+    tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v);
+    for (uint32_t i = 0; i < L::NST; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8); mbar_init(&ds_full[i], 8); }
     mbar_init(res_full, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8);
-      mbar_init(&ds_full[i], 8);  mbar_init(&ds_empty[i], 1);
-    }
+    mbar_init(qdo_ready, 8);
     mbar_init(done, 1);
     fence_mbar_init();
   }
@@ -212,19 +222,19 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  const uint32_t tmem_dQ = tmem_base + 256;
+  const uint32_t tmem_dQ = tmem_base + 256, tmem_Qa = tmem_base + 384, tmem_dOa = tmem_base + 448;
   if (threadIdx.x == 0) AB_TR(1, 1);
 
   if (warp == 0) {
     const int32_t col = head * 128;
     if (elect_one()) {
       mbar_arrive_expect_tx(res_full, 2 * AB_T128);
-      load_tile<128>(sQ, &tmap_q, res_full, col, seq_start + own * 128);
-      load_tile<128>(sdO, &tmap_do, res_full, col, seq_start + own * 128);
+      load_tile<128>(sQdO, &tmap_q, res_full, col, seq_start + own * 128);
+      load_tile<128>(sQdO + AB_T128, &tmap_do, res_full, col, seq_start + own * 128);
     }
     __syncwarp();
     for (uint32_t n = 0; n < n_sub; ++n) {
-      const uint32_t st = n % 3, use = n / 3;
+      const uint32_t st = n % L::NST, use = n / L::NST;
       mbar_wait(&kv_empty[st], (use & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[st], 2 * AB_T64);
@@ -237,12 +247,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     // whole warp runs the issue loop (uniform registers, see elect_one()); one elected lane issues
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 64, 0, 0);    // [128 q] x [64 keys], both K-major over hd
     constexpr uint32_t idesc_dq = umma_idesc_bf16(128, 128, 0, 1);  // dS (K-major over keys) x K_n (MN-major: hd contiguous)
-    const uint64_t q_k = umma_smem_desc_sw128(smem_u32(sQ), 0, 1024);
-    const uint64_t o_k = umma_smem_desc_sw128(smem_u32(sdO), 0, 1024);
-    const uint64_t ds_k = umma_smem_desc_sw128(smem_u32(sDS), 0, 1024);
     auto issue_sdp = [&](uint32_t n) {
-      const uint32_t st = n % 3, b = n & 1;
-      mbar_wait(&kv_full[st], (n / 3) & 1);
+      const uint32_t st = n % L::NST, b = n & 1;
+      mbar_wait(&kv_full[st], (n / L::NST) & 1);
       mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
@@ -251,36 +258,38 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 #pragma unroll
         for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
-          for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_base + b * 64, q_k + ka * (AB_A128 >> 4) + ks * 2, kd + ka * (AB_A64 >> 4) + ks * 2, idesc_s,
+          for (uint32_t ks = 0; ks < 4; ++ks)      // hd step ka*64 + ks*16 -> A columns (ka*32 + ks*8), B bytes as before
+            umma_f16_ts(tmem_base + b * 64, tmem_Qa + ka * 32 + ks * 8, kd + ka * (AB_A64 >> 4) + ks * 2, idesc_s,
                         (ka | ks) ? 1u : 0u);
 #pragma unroll
         for (uint32_t ka = 0; ka < 2; ++ka)
 #pragma unroll
           for (uint32_t ks = 0; ks < 4; ++ks)
-            umma_f16_ss(tmem_base + 128 + b * 64, o_k + ka * (AB_A128 >> 4) + ks * 2, vd + ka * (AB_A64 >> 4) + ks * 2,
-                        idesc_s, (ka | ks) ? 1u : 0u);
+            umma_f16_ts(tmem_base + 128 + b * 64, tmem_dOa + ka * 32 + ks * 8, vd + ka * (AB_A64 >> 4) + ks * 2, idesc_s,
+                        (ka | ks) ? 1u : 0u);
         umma_commit(&sdp_full[b]);
         if (n < 8) AB_TR(1, 10 + 2 * n);
       }
       __syncwarp();
     };
-    mbar_wait(res_full, 0);
+    mbar_wait(qdo_ready, 0);
+    tc_fence_after();
     if (lane == 0) AB_TR(1, 2);
     issue_sdp(0);
     for (uint32_t n = 0; n < n_sub; ++n) {
       if (n + 1 < n_sub) issue_sdp(n + 1);
-      const uint32_t st = n % 3, b = n & 1;
+      const uint32_t st = n % L::NST, b = n & 1;
       mbar_wait(&ds_full[b], (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         if (n < 8) AB_TR(1, 11 + 2 * n);
-        // dQ += dS K_n : contraction over the 64 keys (4 k-steps); B rows = keys, 64-wide hd atoms AB_A64 apart
+        // dQ += dS K_n : contraction over the 64 keys (4 k-steps).  A = dS(n) in the S[b] columns: keys 0..31 at columns
+        // 0..15, keys 32..63 at columns 32..47 (each compute warp overwrote only what it had read).  B rows = keys, 64-wide
+        // hd atoms AB_A64 apart.
         const uint64_t km = umma_smem_desc_sw128(smem_u32(sKV + st * 2 * AB_T64), AB_A64, 1024);
 #pragma unroll
         for (uint32_t ks = 0; ks < 4; ++ks)
-          umma_f16_ss(tmem_dQ, ds_k + b * (AB_PS >> 4) + ks * 2, km + ks * 128, idesc_dq, (n | ks) ? 1u : 0u);
-        umma_commit(&ds_empty[b]);
+          umma_f16_ts(tmem_dQ, tmem_base + b * 64 + (ks >> 1) * 32 + (ks & 1) * 8, km + ks * 128, idesc_dq, (n | ks) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         if (n + 1 == n_sub) umma_commit(done);
       }
@@ -294,9 +303,35 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     const uint32_t qi = own * 128 + r;
     const bool row_valid = qi < (uint32_t)seq_len;
     const int64_t tok = (int64_t)seq_start + qi;
+    // ---- Q, dO -> TMEM (bf16 A-operand layout): this thread owns hd [half*64, half*64+64) of its row = atom `half` of
+    // the TMA-staged tile (two 64-row boxes per atom, 128-byte rows, 16-byte chunks XOR-swizzled by the row) ----
+    {
+      uint32_t a[32], d[32];
+      mbar_wait(res_full, 0);
+      const uint32_t rowoff = half * AB_A128 + (r >> 6) * (64 * 128);
+      const uint32_t qb = smem_u32(sQdO) + rowoff, ob = qb + AB_T128;
+#pragma unroll
+      for (uint32_t i = 0; i < 8; ++i) {
+        const uint32_t o = sw128_offset(r & 63, i);
+        uint4 x, y;
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x.x), "=r"(x.y), "=r"(x.z), "=r"(x.w) : "r"(qb + o));
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(y.x), "=r"(y.y), "=r"(y.z), "=r"(y.w) : "r"(ob + o));
+        if (!row_valid) { x = make_uint4(0, 0, 0, 0); y = make_uint4(0, 0, 0, 0); }   // rows past the sequence: next sequence's data
+        a[4 * i] = x.x; a[4 * i + 1] = x.y; a[4 * i + 2] = x.z; a[4 * i + 3] = x.w;
+        d[4 * i] = y.x; d[4 * i + 1] = y.y; d[4 * i + 2] = y.z; d[4 * i + 3] = y.w;
+      }
+      tmem_st_32x32b_x32(tmem_Qa + lane_off + half * 32, a);
+      tmem_st_32x32b_x32(tmem_dOa + lane_off + half * 32, d);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(qdo_ready);
+    }
     // an invalid row gets LSE = +inf -> p = exp2(-inf) = 0 without a branch
     const float lse_r = row_valid ? lse[(int64_t)head * T + tok] * LOG2E : INFINITY;
     const float d_r = row_valid ? Dvec[(int64_t)head * T + tok] : 0.f;
+    const float2 sl2v = make_float2(sl2, sl2), nl = make_float2(-lse_r, -lse_r);
+    const float2 scv = make_float2(scale, scale), nds = make_float2(-d_r * scale, -d_r * scale);
     for (uint32_t n = 0; n < n_sub; ++n) {
       const uint32_t b = n & 1;
       mbar_wait(&sdp_full[b], (n >> 1) & 1);
@@ -308,26 +343,26 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sdp_empty[b]);           // score buffers may be overwritten by sub-block n+2
+      if (lane == 0) mbar_arrive(&sdp_empty[b]);           // (kept for symmetry; program order already protects S[b])
       const bool diag = (n >= 2 * own);                     // sub-blocks that touch the diagonal 128x128 block
       const uint32_t key0 = n * 64 + half * 32;             // first key of this thread's 32 columns
       uint32_t dd[16];
 #pragma unroll
       for (uint32_t i = 0; i < 32; i += 2) {
-        float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - lse_r);
-        float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - lse_r);
+        float2 e = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, nl);
+        float p0 = exp2f(e.x), p1 = exp2f(e.y);
         if (diag) {
           if (key0 + i > qi) p0 = 0.f;
           if (key0 + i + 1 > qi) p1 = 0.f;
         }
-        dd[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[i]) - d_r) * scale, p1 * (__uint_as_float(dv[i + 1]) - d_r) * scale);
+        // dS = P o (dP - D) * scale
+        const float2 t = __ffma2_rn(make_float2(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), scv, nds);
+        const float2 ds = __fmul2_rn(make_float2(p0, p1), t);
+        dd[i >> 1] = pack_bf16x2(ds.x, ds.y);
       }
-      mbar_wait(&ds_empty[b], ((n >> 1) & 1) ^ 1);         // dQ MMA of sub-block n-2 has consumed this buffer
-      uint8_t* dsb = sDS + b * AB_PS;
-#pragma unroll
-      for (uint32_t q = 0; q < 4; ++q)
-        *reinterpret_cast<uint4*>(dsb + sw128_offset(r, half * 4 + q)) = make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
-      fence_proxy_async_smem();
+      // dS(n) over the S columns this warp has just consumed: keys half*32.. -> 16 packed columns at half*32
+      tmem_st_32x32b_x16(tmem_base + b * 64 + lane_off + half * 32, dd);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ds_full[b]);
@@ -336,7 +371,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     mbar_wait(done, 0);
     if (warp == 2 && lane == 0) AB_TR(1, 50);
     tc_fence_after();
-    uint8_t* stage = sKV;                                   // K/V stages are free: every MMA has completed
+    uint8_t* stage = sQdO;                                  // Q/dO staging is free since qdo_ready
     stage_acc_tile(tmem_dQ, lane_off, half * 32, r, stage);
     compute_warps_sync();
     const uint32_t rows_valid = min(128u, (uint32_t)seq_len - own * 128);
@@ -359,10 +394,8 @@ struct DkvSmem {
   static constexpr uint32_t NST = 3;
   static constexpr uint32_t K_OFF = 0, V_OFF = AB_T128;
   static constexpr uint32_t QO_OFF = 2 * AB_T128;                 // NST x (Q 16K | dO 16K)
-  static constexpr uint32_t PT_OFF = QO_OFF + NST * 2 * AB_T64;   // 16K (single buffer: the accumulate MMAs of sub-block n
-  static constexpr uint32_t DST_OFF = PT_OFF + AB_PS;             // 16K  finish long before sub-block n+1 is ready to store)
-  static constexpr uint32_t BAR_OFF = DST_OFF + AB_PS;
-  // res_full, qo_full[3], qo_empty[3], sdp_full[2], sdp_empty[2], pds_full, pds_empty, done
+  static constexpr uint32_t BAR_OFF = QO_OFF + NST * 2 * AB_T64;
+  // res_full, qo_full[3], qo_empty[3], sdp_full[2], sdp_empty[2], pds_full[2], done
   static constexpr uint32_t NUM_BARS = 14;
   static constexpr uint32_t DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
@@ -380,16 +413,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* sK = smem + L::K_OFF;
   uint8_t* sV = smem + L::V_OFF;
   uint8_t* sQO = smem + L::QO_OFF;
-  uint8_t* sPT = smem + L::PT_OFF;
-  uint8_t* sDST = smem + L::DST_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* res_full = bars + 0;
   uint64_t* qo_full = bars + 1;     // [3]
   uint64_t* qo_empty = bars + 4;    // [3]
   uint64_t* sdp_full = bars + 7;    // [2]
   uint64_t* sdp_empty = bars + 9;   // [2]
-  uint64_t* pds_full = bars + 11;
-  uint64_t* pds_empty = bars + 12;
+  uint64_t* pds_full = bars + 11;   // [2] P^T(n) / dS^T(n) are in TMEM (over S^T[b] / dP^T[b])
   uint64_t* done = bars + 13;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
   __shared__ float s_stats[8][2][32];   // per compute warp: LSE*log2e and D of its 32 query columns
@@ -415,8 +445,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     mbar_init(res_full, 1);
     for (int i = 0; i < 3; ++i) { mbar_init(&qo_full[i], 1); mbar_init(&qo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8); }
-    mbar_init(pds_full, 8);
-    mbar_init(pds_empty, 1);
+    mbar_init(&pds_full[0], 8); mbar_init(&pds_full[1], 8);
     mbar_init(done, 1);
     fence_mbar_init();
   }
@@ -452,8 +481,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     constexpr uint32_t idesc_acc = umma_idesc_bf16(128, 128, 0, 1);  // P^T/dS^T (K-major over q) x dO_n/Q_n (MN-major)
     const uint64_t k_k = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
     const uint64_t v_k = umma_smem_desc_sw128(smem_u32(sV), 0, 1024);
-    const uint64_t pt_k = umma_smem_desc_sw128(smem_u32(sPT), 0, 1024);
-    const uint64_t dst_k = umma_smem_desc_sw128(smem_u32(sDST), 0, 1024);
     auto issue_sdp = [&](uint32_t n) {
       const uint32_t st = n % 3, b = n & 1;
       mbar_wait(&qo_full[st], (n / 3) & 1);
@@ -484,19 +511,23 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     issue_sdp(0);
     for (uint32_t n = 0; n < n_it; ++n) {
       if (n + 1 < n_it) issue_sdp(n + 1);
-      const uint32_t st = n % 3;
-      mbar_wait(pds_full, n & 1);
+      const uint32_t st = n % 3, b = n & 1;
+      mbar_wait(&pds_full[b], (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         if (n < 8) AB_TR(0, 11 + 2 * n);
-        // contraction over the 64 queries (4 k-steps); B rows = queries, 64-wide hd atoms AB_A64 apart
+        // contraction over the 64 queries (4 k-steps).  A operands in TENSOR MEMORY (.ts form): P^T(n) lies over the
+        // S^T[b] columns it was computed from, dS^T(n) over dP^T[b] (queries 0..31 at columns 0..15, 32..63 at 32..47: each
+        // compute warp overwrote only what it had read) - no smem store, no proxy fence, no A-operand smem bandwidth.
+        // B rows = queries, 64-wide hd atoms AB_A64 apart.
         const uint64_t qm = umma_smem_desc_sw128(smem_u32(sQO + st * 2 * AB_T64), AB_A64, 1024);
         const uint64_t om = qm + (AB_T64 >> 4);
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dV, pt_k + ks * 2, om + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
+        for (uint32_t ks = 0; ks < 4; ++ks)
+          umma_f16_ts(tmem_dV, tmem_base + b * 64 + (ks >> 1) * 32 + (ks & 1) * 8, om + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ss(tmem_dK, dst_k + ks * 2, qm + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
-        umma_commit(pds_empty);
+        for (uint32_t ks = 0; ks < 4; ++ks)
+          umma_f16_ts(tmem_dK, tmem_base + 128 + b * 64 + (ks >> 1) * 32 + (ks & 1) * 8, qm + ks * 128, idesc_acc, (n | ks) ? 1u : 0u);
         umma_commit(&qo_empty[st]);
         if (n + 1 == n_it) umma_commit(done);
       }
@@ -518,10 +549,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       const uint32_t qi = (first + n) * 64 + half * 32 + lane;
       const bool ok = qi < (uint32_t)seq_len;
       const int64_t tq = (int64_t)seq_start + qi;
-      l_out = ok ? lse[(int64_t)head * T + tq] * LOG2E : INFINITY;   // +inf -> p = 0 for rows past the sequence
-      d_out = ok ? Dvec[(int64_t)head * T + tq] : 0.f;
+      // stored NEGATED / pre-scaled so that the loop is two packed FMAs: -inf -> p = exp2(-inf) = 0 for rows past the sequence
+      l_out = ok ? -lse[(int64_t)head * T + tq] * LOG2E : -INFINITY;
+      d_out = ok ? -Dvec[(int64_t)head * T + tq] * scale : 0.f;
     };
-    float cur_l = INFINITY, cur_d = 0.f;
+    float cur_l = -INFINITY, cur_d = 0.f;
+    const float2 sl2v = make_float2(sl2, sl2), scv = make_float2(scale, scale);
     if (n_it > 0) load_stats(0, cur_l, cur_d);
     for (uint32_t n = 0; n < n_it; ++n) {
       const uint32_t b = n & 1;
@@ -545,30 +578,26 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
       uint32_t pp[16], dd[16];
 #pragma unroll
       for (uint32_t i = 0; i < 32; i += 2) {
-        const float2 l2 = *reinterpret_cast<const float2*>(st_l + i);
-        const float2 d2 = *reinterpret_cast<const float2*>(st_d + i);
-        float p0 = exp2f(__uint_as_float(sv[i]) * sl2 - l2.x);
-        float p1 = exp2f(__uint_as_float(sv[i + 1]) * sl2 - l2.y);
+        const float2 l2 = *reinterpret_cast<const float2*>(st_l + i);       // -LSE * log2e of queries i, i+1
+        const float2 d2 = *reinterpret_cast<const float2*>(st_d + i);       // -D * scale
+        const float2 e = __ffma2_rn(make_float2(__uint_as_float(sv[i]), __uint_as_float(sv[i + 1])), sl2v, l2);
+        float p0 = exp2f(e.x), p1 = exp2f(e.y);
         if (diag) {                                         // causal: a query sees keys <= itself
           if (q0 + i < kj) p0 = 0.f;
           if (q0 + i + 1 < kj) p1 = 0.f;
         }
         pp[i >> 1] = pack_bf16x2(p0, p1);
-        dd[i >> 1] = pack_bf16x2(p0 * (__uint_as_float(dv[i]) - d2.x) * scale, p1 * (__uint_as_float(dv[i + 1]) - d2.y) * scale);
+        const float2 t = __ffma2_rn(make_float2(__uint_as_float(dv[i]), __uint_as_float(dv[i + 1])), scv, d2);   // (dP - D) * scale
+        const float2 ds = __fmul2_rn(make_float2(p0, p1), t);
+        dd[i >> 1] = pack_bf16x2(ds.x, ds.y);
       }
-      mbar_wait(pds_empty, (n & 1) ^ 1);                   // accumulate MMAs of sub-block n-1 have consumed P^T / dS^T
-      uint8_t* ptb = sPT;
-      uint8_t* dsb = sDST;
-#pragma unroll
-      for (uint32_t q = 0; q < 4; ++q) {
-        const uint32_t off = sw128_offset(r, half * 4 + q);
-        *reinterpret_cast<uint4*>(ptb + off) = make_uint4(pp[q * 4], pp[q * 4 + 1], pp[q * 4 + 2], pp[q * 4 + 3]);
-        *reinterpret_cast<uint4*>(dsb + off) = make_uint4(dd[q * 4], dd[q * 4 + 1], dd[q * 4 + 2], dd[q * 4 + 3]);
-      }
-      fence_proxy_async_smem();
+      // P^T(n) / dS^T(n) straight into TMEM, over the score columns this warp has just consumed (queries half*32..)
+      tmem_st_32x32b_x16(tmem_base + b * 64 + lane_off + half * 32, pp);
+      tmem_st_32x32b_x16(tmem_base + 128 + b * 64 + lane_off + half * 32, dd);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
+      if (lane == 0) mbar_arrive(&pds_full[b]);
       if (warp == 2 && lane == 0 && n < 8) AB_TR(0, 31 + 2 * n);
     }
     mbar_wait(done, 0);
@@ -652,7 +681,7 @@ extern "C" int nv_attn_bwd(const void* q, int64_t ldq, const void* k, int64_t ld
       cu_seqlens, B, T, scale, rope_pos, c, s);
   NV_LAUNCH_CHECK();
   attn_bwd_dq_kernel<<<grid, AB_THREADS, DqSmem::DYN_BYTES, stream>>>(
-      tq, tk, tv, tdo, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dq), lddq, cu_seqlens, B, T, scale, rope_pos, c, s);
+      tq, tdo, tk, tv, lse, dvec, reinterpret_cast<__nv_bfloat16*>(dq), lddq, cu_seqlens, B, T, scale, rope_pos, c, s);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

@@ -164,11 +164,20 @@ class FlatParams:
     def offset_of(self, p: nn.Parameter) -> int:
         return self.offsets[next(k for k, q in enumerate(self.params) if q is p)]
 
+    def rebind_grads(self, new_flat_grad: torch.Tensor) -> None:
+        """Move the gradient buffer (e.g. into a symmetric NVLS allocation): same layout, ``p.grad`` re-viewed."""
+        assert new_flat_grad.numel() == self.flat_grad.numel() and new_flat_grad.dtype == self.flat_grad.dtype
+        self.flat_grad = new_flat_grad
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+
     def reattach_grads(self) -> None:
         """After ``optimizer.zero_grad(set_to_none=True)``: zero the buffer and hand the views back."""
         self.flat_grad.zero_()
         for p, o in zip(self.params, self.offsets):
             p.grad = self.flat_grad[o:o + p.numel()].view(p.shape)
+        if getattr(self, "on_zeroed", None) is not None:
+            self.on_zeroed()
 
     def _fused_span(self, members, shape):
         """Offset / size of the fused view over ``members`` (parameters that must sit back to back, in this order, in the
@@ -254,6 +263,17 @@ class LlamaCore:
             self.gd.append(m.down_proj.weight.grad)
         self.cos, self.sin = rope_tables(dims, flat.flat.device)
         self.fused_epilogues = True
+
+    def refresh_grad_views(self) -> None:
+        """Re-derive the fused gradient views after ``FlatParams.rebind_grads``."""
+        D, F = self.d.hidden, self.d.inter
+        flat = self.flat
+        for l, lyr in enumerate(self.model.layers):
+            a, m = lyr.self_attn, lyr.mlp
+            self.gqkv[l] = flat.grad_view([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], (3 * D, D))
+            self.go[l] = a.o_proj.weight.grad
+            self.ggu[l] = flat.grad_view([m.gate_proj.weight, m.up_proj.weight], (2 * F, D))
+            self.gd[l] = m.down_proj.weight.grad
 
     # -------------------------------------------------------------------------------------------------
     def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True, kv_sink=None,

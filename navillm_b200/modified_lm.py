@@ -230,6 +230,7 @@ class _LMFn(torch.autograd.Function):
             dy = dout.contiguous().to(bf16)
         else:
             g, rstd, hn, dlogits = ctx.saved
+            lm._lm_head_grad_clean = False
             # dlogits was produced with scale 1/N; fold the incoming scalar gradient in on the device (no sync)
             dlogits.copy_(dlogits.float() * dout.float())        # in place: keeps the 16-byte-aligned row stride
             dy = ops.gemm(dlogits, lm.lm_head.weight.data, b_mn=True)                    # [Nl, D]
@@ -333,6 +334,9 @@ class ModifiedLlamaForCausalLM(nn.Module):
         params = self.lm_parameters() + list(getattr(self, "_extra_params", []))
         self.__dict__.pop("_decode_states", None)     # captured decode graphs hold pointers into the old buffers
         self.flat = FlatParams(params, device)
+        self.flat.clean_segments = self._clean_grad_segments
+        self.flat.on_zeroed = self.mark_grads_zeroed
+        self._lm_head_grad_clean = False             # unknown until the next zero_grad
         self.core = LlamaCore(self.dims, self.model, self.flat)
         self.special_ids_dev = torch.tensor(self.special_token_ids, dtype=torch.int32, device=device)
         return self.flat
@@ -349,6 +353,17 @@ class ModifiedLlamaForCausalLM(nn.Module):
         flat, layers = self.flat, self.model.layers
         starts = [flat.offset_of(l.self_attn.q_proj.weight) for l in layers] + [flat.offset_of(self.model.embed_tokens.weight)]
         return self.grad_sync.layer_hook(flat, starts, self.dims.n_layers)
+
+    def _clean_grad_segments(self):
+        """Flat-gradient ranges known to be all-zero (see GradSync.exchange): lm_head after a zero_grad when no LM-loss
+        backward has run since (navigation / grounding steps never touch it)."""
+        if not getattr(self, "_lm_head_grad_clean", False):
+            return []
+        o = self.flat.offset_of(self.lm_head.weight)
+        return [(o, o + self.lm_head.weight.numel())]
+
+    def mark_grads_zeroed(self) -> None:
+        self._lm_head_grad_clean = True
 
     def _own_flats(self):
         return [(self.flat, self.flat.offset_of(self.model.embed_tokens.weight))] if self.core is not None else []

@@ -254,6 +254,19 @@ class NavModel(nn.Module):
         lm = self.lang_model
         return [(lm.flat, lm.flat.offset_of(lm.model.embed_tokens.weight)), (self._flat32, None)]
 
+    def adopt_symmetric_grads(self, reducer):
+        """Move both flat gradient buffers into symmetric (NVLS multicast) allocations for the in-switch exchange of
+        navillm_b200.parallel.NvlsReducer.  Collective: every rank calls it (the DDP wrapper does)."""
+        self._ensure()
+        lm = self.lang_model
+
+        def rebind_lm(buf):
+            lm.flat.rebind_grads(buf)
+            lm.core.refresh_grad_views()
+        reducer.adopt(lm.flat, rebind_lm)
+        reducer.adopt(self._flat32, self._flat32.rebind_grads)
+        return reducer
+
     def _settle_lazy_zero(self) -> None:
         """``zero_grad(lazy=True)`` promised that the next LM backward overwrites the per-layer gradients.  If an
         exchange or an optimizer step arrives with no LM backward in between (a skipped / guarded iteration), the stale
@@ -290,6 +303,7 @@ class NavModel(nn.Module):
             lm.flat.overwrite_layer_grads = True
         else:
             lm.flat.flat_grad.zero_()
+        lm.mark_grads_zeroed()
 
     def _anchor_t(self):
         return self._anchor.detach().requires_grad_(torch.is_grad_enabled())

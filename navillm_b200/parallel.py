@@ -30,6 +30,7 @@ holds; torch's reducer is never constructed.
 from __future__ import annotations
 
 import contextlib
+import os
 from typing import Callable, List, Optional
 
 import torch
@@ -41,6 +42,63 @@ def _dist():
     return dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
 
 
+class NvlsReducer:
+    """In-switch all-reduce of flat gradient buffers over NVLS multicast (csrc/nvls_allreduce.cu) on a side stream.
+
+    ``adopt(flat)`` moves a FlatParams gradient buffer into a SYMMETRIC allocation (torch.distributed._symmetric_memory:
+    same size on every rank, bound to one multicast object) -- a collective call.  ``all_reduce(flat, a, b)`` then enqueues,
+    on the side stream and ordered after everything the current stream has done so far:
+        barrier (all replicas of the range are complete)  ->  nv_multimem_allreduce  ->  barrier (all parts are stored)
+    and returns a CUDA event the consumer waits for.  Rank r reduces the r-th 1/W of the range: multimem.ld_reduce pulls
+    the sum of the W replicas out of the switch, multimem.st pushes the average back into all of them."""
+
+    def __init__(self, ctas: int = 0):
+        self.stream = torch.cuda.Stream()
+        self.handles = {}
+        self.ctas = ctas or int(os.environ.get("NAVILLM_NVLS_CTAS", "32"))
+        self.n_reduced = 0
+
+    @staticmethod
+    def wanted() -> bool:
+        dist = _dist()
+        return dist is not None and dist.get_backend() == "nccl" and os.environ.get("NAVILLM_NVLS", "1") != "0"
+
+    def adopt(self, flat, rebind) -> None:
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        buf = symm.empty(flat.flat_grad.numel(), dtype=flat.dtype, device=flat.flat.device)
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        if not getattr(hdl, "multicast_ptr", 0):
+            raise RuntimeError("symmetric memory has no NVLS multicast mapping on this system")
+        buf.copy_(flat.flat_grad)
+        rebind(buf)                                   # p.grad views (and the fused grad views) now live in `buf`
+        self.handles[id(flat)] = (hdl, buf)
+
+    def has(self, flat) -> bool:
+        return id(flat) in self.handles
+
+    def all_reduce(self, flat, a: int, b: int, scale: float):
+        from . import _lib
+        hdl, buf = self.handles[id(flat)]
+        if flat.flat_grad.data_ptr() != buf.data_ptr():
+            raise RuntimeError("the symmetric gradient buffer was replaced (re-materialised model?): re-wrap the model")
+        cur = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(cur)
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            hdl.barrier(channel=0)
+            _lib.check(_lib.load().nv_multimem_allreduce(_lib.ctypes.c_uint64(int(hdl.multicast_ptr)), _lib.i64(a), _lib.i64(b - a),
+                                                         _lib.i32(1 if flat.dtype == torch.bfloat16 else 0), _lib.i32(hdl.rank),
+                                                         _lib.i32(hdl.world_size), _lib.f32(scale), _lib.i32(self.ctas),
+                                                         _lib.ctypes.c_void_p(self.stream.cuda_stream)), "nv_multimem_allreduce")
+            hdl.barrier(channel=0)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        self.n_reduced += 1
+        return done
+
+
 class GradSync:
     """State machine of the gradient exchange of ONE model replica (shared by NavModel and its language model)."""
 
@@ -48,10 +106,11 @@ class GradSync:
         self.armed = False            # the last grad-enabled forward ran outside no_sync()
         self.queued = False           # the end-of-backward callback of the running pass is queued
         self.overlap = True           # reduce finished layer groups while the backward is still running
-        self.chunk_layers = 4
+        self.chunk_layers = int(os.environ.get("NAVILLM_SYNC_CHUNK", "2"))   # decoder layers per overlapped reduction
         self.flats: Callable[[], list] = lambda: []          # -> [(FlatParams, tail_offset or None), ...]
         self._pending: List[tuple] = []
         self._lm_layers_reduced = False
+        self.reducer: Optional[NvlsReducer] = None            # set by the DDP wrapper when NVLS multicast is available
         self.stats = {"collectives": 0, "exchanges": 0, "async_slices": 0}
 
     # ---- forward side -------------------------------------------------------------------------------------------
@@ -76,19 +135,34 @@ class GradSync:
         avg = dist.ReduceOp.AVG if dist.get_backend() == "nccl" else dist.ReduceOp.SUM
         ws = dist.get_world_size()
         self._lm_layers_reduced = True
+        # group boundaries: every `chunk` layers, and the LAST group (layers chunk-1 .. 0, finished when the backward is
+        # almost over, so its reduction is mostly exposed) is cut into single layers
+        ends = {l: min(l + chunk, n_layers) for l in range(0, n_layers, chunk)}
+        for l in range(1, min(chunk, n_layers)):
+            ends[l] = l + 1
+        if chunk > 1 and n_layers > 0:
+            ends[0] = 1
+
+        nvls = self.reducer if (self.reducer is not None and self.reducer.has(flat)) else None
 
         def done(l: int) -> None:
-            if l % chunk != 0:
+            if l not in ends:
                 return
-            sl = flat.flat_grad[starts[l]:starts[min(l + chunk, n_layers)]]
-            h = dist.all_reduce(sl, op=avg, async_op=True)
-            self._pending.append((h, sl if avg == dist.ReduceOp.SUM else None, ws))
+            if nvls is not None:                                  # in-switch reduction on the side stream
+                self._pending.append((nvls.all_reduce(flat, starts[l], starts[ends[l]], 1.0 / ws), None, ws))
+            else:
+                sl = flat.flat_grad[starts[l]:starts[ends[l]]]
+                h = dist.all_reduce(sl, op=avg, async_op=True)
+                self._pending.append((h, sl if avg == dist.ReduceOp.SUM else None, ws))
             self.stats["collectives"] += 1
             self.stats["async_slices"] += 1
         return done
 
     def _drain(self) -> None:
         for h, sl, ws in self._pending:
+            if isinstance(h, torch.cuda.Event):
+                torch.cuda.current_stream().wait_event(h)
+                continue
             h.wait()
             if sl is not None:
                 sl.div_(ws)
@@ -114,11 +188,32 @@ class GradSync:
         for flat, tail in self.flats():
             if flat is None:
                 continue
-            buf = flat.flat_grad[tail:] if (covered_lm_layers and tail is not None) else flat.flat_grad
-            dist.all_reduce(buf, op=avg)
-            if avg == dist.ReduceOp.SUM:
-                buf.div_(ws)
-            n += 1
+            lo = tail if (covered_lm_layers and tail is not None) else 0
+            hi = flat.flat_grad.numel()
+            # segments that no backward has written since they were zeroed are zero on EVERY rank (the decision is taken
+            # from the call sequence, which the reference keeps identical on all ranks: tasks/loaders.py:179 broadcasts the
+            # task): their average is zero, nothing to exchange.  In the navigation / grounding modes that is lm_head
+            # (262 MB, half of what the overlapped layer reductions leave for the end of the backward).
+            ranges, cur = [], lo
+            for a, b in sorted(getattr(flat, "clean_segments", lambda: [])()):
+                a, b = max(a, lo), min(b, hi)
+                if a >= b:
+                    continue
+                if a > cur:
+                    ranges.append((cur, a))
+                cur = max(cur, b)
+            if cur < hi:
+                ranges.append((cur, hi))
+            for a, b in ranges:
+                if self.reducer is not None and self.reducer.has(flat):
+                    self._pending.append((self.reducer.all_reduce(flat, a, b, 1.0 / ws), None, ws))
+                else:
+                    buf = flat.flat_grad[a:b]
+                    dist.all_reduce(buf, op=avg)
+                    if avg == dist.ReduceOp.SUM:
+                        buf.div_(ws)
+                n += 1
+        self._drain()
         self.stats["collectives"] += n
         self.stats["exchanges"] += 1
         return n
@@ -142,6 +237,15 @@ class DistributedDataParallel(torch.nn.parallel.DistributedDataParallel):
         self.require_backward_grad_sync = True
         if broadcast_parameters:
             self.broadcast_parameters()
+        self.nvls = False
+        if NvlsReducer.wanted() and hasattr(module, "adopt_symmetric_grads"):
+            try:
+                module.grad_sync.reducer = module.adopt_symmetric_grads(NvlsReducer())
+                self.nvls = module.grad_sync.reducer is not None
+            except Exception as e:                    # no multicast support / symmetric memory unavailable: NCCL path
+                import warnings
+                warnings.warn(f"navillm_b200: NVLS gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
+                module.grad_sync.reducer = None
 
     def broadcast_parameters(self, src: int = 0) -> None:
         """DDP's construction-time parameter broadcast: one broadcast per flat weight buffer once they exist

@@ -38,6 +38,43 @@ def _rollout(model, g, dev, n_steps, B=2):
                 (og["obj_logits"].float().logsumexp(-1).sum() * 0.1).backward()
 
 
+def _nvls_unit(rank, world, dev):
+    """nv_multimem_allreduce on random data against the arithmetic it promises: fp32 sum of the replicas' bf16 values,
+    times 1/world, rounded once to bf16 (bit-exact for world = 2: the sum of two bf16 numbers is exact in fp32)."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm
+    from navillm_b200 import _lib
+    n = 1 << 20
+    results = {}
+    for dtype in (torch.bfloat16, torch.float32):
+        buf = symm.empty(n, dtype=dtype, device=dev)
+        hdl = symm.rendezvous(buf, dist.group.WORLD)
+        assert hdl.multicast_ptr, "no NVLS multicast mapping"
+        g = torch.Generator(device=dev).manual_seed(100 + rank)
+        buf.copy_(torch.randn(n, generator=g, device=dev).to(dtype))
+        mine = buf.float().clone()
+        ref = mine.clone()
+        dist.all_reduce(ref)                                   # fp32 NCCL sum of the same values
+        ref = (ref / world).to(dtype)
+        off, cnt = 1024, n - 4096                              # an interior, 16-byte aligned range
+        torch.cuda.synchronize()
+        hdl.barrier(channel=0)
+        _lib.check(_lib.load().nv_multimem_allreduce(_lib.ctypes.c_uint64(int(hdl.multicast_ptr)), _lib.i64(off), _lib.i64(cnt),
+                                                     _lib.i32(1 if dtype == torch.bfloat16 else 0), _lib.i32(rank), _lib.i32(world),
+                                                     _lib.f32(1.0 / world), _lib.i32(16), _lib.stream_ptr()), "nv_multimem_allreduce")
+        hdl.barrier(channel=0)
+        torch.cuda.synchronize()
+        got = buf.clone()
+        inside = slice(off, off + cnt)
+        err = (got[inside].float() - ref[inside].float()).abs().max().item()
+        lim = 0.0 if world == 2 else (2.0 ** -7 if dtype == torch.bfloat16 else 1e-6) * ref.float().abs().max().item()
+        assert err <= lim, f"rank {rank} {dtype}: multimem all-reduce differs from the NCCL fp32 reference by {err}"
+        # outside the range nothing was touched
+        assert torch.equal(got[:off].float(), mine[:off]) and torch.equal(got[off + cnt:].float(), mine[off + cnt:])
+        results[str(dtype)] = err
+    return results
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -54,15 +91,31 @@ def _worker(rank, world, port, q):
     _rollout(bare, g, dev, n_steps)                                     # local accumulation only
     torch.cuda.synchronize()
     local = {n: p.grad.detach().float().clone() for n, p in bare.named_parameters() if p.grad is not None}
-    for overlap in (True, False):
+    nvls_ok = True
+    try:
+        _nvls_unit(rank, world, dev)
+    except Exception as e:                                    # no multicast support on this box: the NCCL path is still tested
+        nvls_ok = False
+        if rank == 0:
+            print(f"[nvls unit] unavailable: {type(e).__name__}: {e}")
+    flags = [None] * world
+    dist.all_gather_object(flags, nvls_ok)
+    nvls_ok = all(flags)
+    for overlap, nvls in ((True, False), (False, False), (True, True), (False, True)):
+        if nvls and not nvls_ok:
+            continue
+        os.environ["NAVILLM_NVLS"] = "1" if nvls else "0"
         m, _ = build_model(g, dev)
         m.train(False)
         m.grad_sync.overlap, m.grad_sync.chunk_layers = overlap, 1
         model = DDP(m, device_ids=[rank], find_unused_parameters=True)   # tools/optims.py:54
+        assert model.nvls == nvls, (model.nvls, nvls)
         _rollout(model, g, dev, n_steps)
         torch.cuda.synchronize()
         st = dict(m.grad_sync.stats)
         assert st["exchanges"] == 2 and (st["async_slices"] > 0) == overlap, st
+        if rank == 0:
+            print(f"[ddp overlap={overlap} nvls={nvls}] {st}")
         named = dict(m.named_parameters())
         worst = 0.0
         for n, gl in local.items():

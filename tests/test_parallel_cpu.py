@@ -123,7 +123,8 @@ def _worker(rank, world, port, q, overlap):
     assert counts[0] == counts[1], f"ranks issued different collectives: {counts}"   # equal although rollout lengths differ
     assert st["exchanges"] == 4                                       # 2 iterations x (navigation + object grounding)
     if overlap:
-        assert st["async_slices"] == 4 * (N_LAYERS // 2) and st["collectives"] == 4 * (N_LAYERS // 2 + 2)
+        # groups of 2 layers, the last group cut into single layers: 8 layers -> slices at l = 6, 4, 2, 1, 0
+        assert st["async_slices"] == 4 * (N_LAYERS // 2 + 1) and st["collectives"] == 4 * (N_LAYERS // 2 + 1 + 2)
     else:
         assert st["async_slices"] == 0 and st["collectives"] == 4 * 2          # ONE collective per flat buffer per exchange
     # a validate-style forward with no backward, then a no_sync pass: must not exchange (DDP decides at the LAST forward)
