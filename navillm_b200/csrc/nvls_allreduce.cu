@@ -42,23 +42,34 @@ __global__ void __launch_bounds__(512) multimem_allreduce_kernel(uint64_t mc_bas
   const int64_t per = (n_chunks + world - 1) / world;
   const int64_t c0 = min((int64_t)rank * per, n_chunks), c1 = min(c0 + per, n_chunks);
   const uint64_t base = mc_base + (uint64_t)byte_off;
-  for (int64_t c = c0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c1; c += (int64_t)gridDim.x * blockDim.x) {
-    const uint64_t a = base + (uint64_t)c * 16u;
-    uint32_t v[4];
-    if (BF16) {
-      mm_ld_reduce_bf16x2(a, v);
-      if (scale != 1.f) {
+  // four independent chunks per thread and iteration: a multimem round trip through the switch takes microseconds, the
+  // bandwidth comes from bytes in flight, and the CTA count has to stay small (the CTAs share SMs with the persistent
+  // wgrad GEMMs: every SM they claim is taken from a CTA pair)
+  constexpr int U = 4;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t c = c0 + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; c < c1; c += stride * U) {
+    uint32_t v[U][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = pack_bf16x2(bf16_lo(v[i]) * scale, bf16_hi(v[i]) * scale);
-      }
-    } else {
-      mm_ld_reduce_f32(a, v);
-      if (scale != 1.f) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * scale);
+    for (int u = 0; u < U; ++u) {
+      const int64_t cc = c + u * stride;
+      if (cc < c1) {
+        if (BF16) mm_ld_reduce_bf16x2(base + (uint64_t)cc * 16u, v[u]);
+        else mm_ld_reduce_f32(base + (uint64_t)cc * 16u, v[u]);
       }
     }
-    mm_st_16(a, v);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t cc = c + u * stride;
+      if (cc < c1) {
+        if (scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            v[u][i] = BF16 ? pack_bf16x2(bf16_lo(v[u][i]) * scale, bf16_hi(v[u][i]) * scale)
+                           : __float_as_uint(__uint_as_float(v[u][i]) * scale);
+        }
+        mm_st_16(base + (uint64_t)cc * 16u, v[u]);
+      }
+    }
   }
 }
 

@@ -55,7 +55,7 @@ class NvlsReducer:
     def __init__(self, ctas: int = 0):
         self.stream = torch.cuda.Stream()
         self.handles = {}
-        self.ctas = ctas or int(os.environ.get("NAVILLM_NVLS_CTAS", "32"))
+        self.ctas = ctas or int(os.environ.get("NAVILLM_NVLS_CTAS", "8"))
         self.n_reduced = 0
 
     @staticmethod

@@ -40,7 +40,8 @@ def _rollout(model, g, dev, n_steps, B=2):
 
 def _nvls_unit(rank, world, dev):
     """nv_multimem_allreduce on random data against the arithmetic it promises: fp32 sum of the replicas' bf16 values,
-    times 1/world, rounded once to bf16 (bit-exact for world = 2: the sum of two bf16 numbers is exact in fp32)."""
+    times 1/world, rounded once to bf16 -- to one bf16 ulp: the switch rounds its fp32 accumulator to bf16 in its own way
+    (measured: 1-ulp differences against round-to-nearest-even of the fp32 NCCL sum)."""
     import torch.distributed as dist
     import torch.distributed._symmetric_memory as symm
     from navillm_b200 import _lib
@@ -67,7 +68,7 @@ def _nvls_unit(rank, world, dev):
         got = buf.clone()
         inside = slice(off, off + cnt)
         err = (got[inside].float() - ref[inside].float()).abs().max().item()
-        lim = 0.0 if world == 2 else (2.0 ** -7 if dtype == torch.bfloat16 else 1e-6) * ref.float().abs().max().item()
+        lim = (2.0 ** -7 if dtype == torch.bfloat16 else 1e-6) * ref.float().abs().max().item()
         assert err <= lim, f"rank {rank} {dtype}: multimem all-reduce differs from the NCCL fp32 reference by {err}"
         # outside the range nothing was touched
         assert torch.equal(got[:off].float(), mine[:off]) and torch.equal(got[off + cnt:].float(), mine[off + cnt:])
