@@ -7,7 +7,11 @@ Workloads (BASELINE.json `configs`):
   c2 (default; configs[1], the configuration the metric is quoted on): R2R-shaped training step, B=16 per GPU, 36 x 1408
      views, hist=8, 24 graph nodes, 15 candidates + stop, prompt lengths U{256..1024}.  One "step" = one batch of 16
      navigation steps: model('panorama') -> model('navigation') -> CE(fuse_logits, targets) -> backward.  nav-steps/s.
+  c1 (configs[0], the reference's own CPU-runnable case): ONE navigation step, forward only, batch=1; `--impl reference`
+     runs the FULL 32-layer oracle port on the host cores for it (no layer scaling).
   c5 (configs[4] per rank): CVDN long horizon, B=4 per GPU, hist=40, 64 graph nodes, 24 candidates, dense S=2048.
+  c4 (configs[3] per rank): multi-task mixed batch, 8 samples per GPU as 4 micro-batches (R2R, CVDN, SOON + object grounding,
+     ScanQA LM loss) accumulated under no_sync() with ONE gradient exchange per step; samples/s.
   c3 (configs[2]): ScanQA-shaped greedy generation, B=8 per GPU, 256 <cand> + 64 text tokens, 128 new tokens;
      tokens/s, prefill ms, ms/token and the HBM roofline of the CUDA-graph decode step.
 `value` times the step with all inputs resident in HBM; `e2e` times the same call sequence through the public API from
@@ -56,11 +60,18 @@ WORKLOADS = {
     "c5": dict(B=4, n_hist=40, n_gmap=64, n_cand=24, len_lo=2048, len_hi=2048, max_length=4096,
                name="C5 CVDN long-horizon training step (panorama+navigation fwd+bwd), B=4/GPU (32 on 8 GPUs), 36x1408 views, hist=40, "
                     "64 graph nodes, 23 candidates, dense seq=2048, Vicuna-7B random init"),
+    "c1": dict(B=1, n_hist=0, n_gmap=4, n_cand=4, len_lo=192, len_hi=192, max_length=1024,
+               name="C1 single navigation step FORWARD only (plumbing config): batch=1, 36x1408 views, 64-token instruction + prompt "
+                    "boilerplate (S=192), 3 candidates + stop, Vicuna-7B random init"),
+    "c4": dict(B=8, name="C4 multi-task mixed step (fwd+bwd, gradient accumulation over 4 micro-batches of 2 samples per GPU: R2R hist=8 "
+                         "S<=512; CVDN hist=20 S<=1024; SOON hist=10 S<=768 + object grounding over 40 objects; ScanQA 36 <cand> + "
+                         "16-token answer LM loss), 8 samples/GPU = global batch 64 on 8 GPUs, Vicuna-7B random init"),
     "c3": dict(B=8, n_cand_tok=256, n_text=64, n_new=128,
                name="C3 ScanQA-shaped greedy generate, B=8/GPU, 256 <cand> visual tokens + 64 text tokens (S0=320), 128 new tokens, "
                     "Vicuna-7B random init"),
 }
 
+C4_MEAN_LEN = 520           # mean prompt length of the four C4 micro-batch shapes (384, 768, 576, ~350)
 T0 = time.time()
 
 
@@ -87,6 +98,24 @@ def gemm_traffic():
     return (tot / n if n else None), f"mean over {n} captured launches, {p.name}"
 
 
+def decode_traffic(n_layers: int):
+    """DRAM bytes of one decode step from the committed `ncu --set full` capture of the decode kernels
+    (profiles/r0N_decode_ncu_summary.json): the first five captured launches are one layer's set in stream order (o_proj,
+    gate|up + SwiGLU, down_proj, next layer's qkv, decode attention; the row kernels move < 1 MB); lm_head is added at its
+    algorithmic size."""
+    cands = sorted((ROOT / "profiles").glob("r0*_decode_ncu_summary.json"))
+    if not cands:
+        return None, None
+    unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+    ks = json.loads(cands[-1].read_text())["kernels"][:5]
+    per_layer = 0.0
+    for k in ks:
+        for key in ("dram_read", "dram_write"):
+            v, u = k[key].split()
+            per_layer += float(v) * unit[u]
+    return per_layer * n_layers + 2.0 * (VOCAB + 6) * D_MODEL, f"{cands[-1].name}: 5 launches = one layer, x{n_layers} + lm_head"
+
+
 def peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -106,6 +135,7 @@ def make_workload(seed: int, B: int = None, n_hist: int = None, n_gmap: int = No
     n_cand = N_CAND if n_cand is None else n_cand
     len_lo = LEN_LO if len_lo is None else len_lo
     len_hi = LEN_HI if len_hi is None else len_hi
+    assert n_gmap == 1 + n_hist + (n_cand - 1), "graph = stop + visited (history) + current candidates (one <cand> token each)"
     rng = np.random.RandomState(seed)
     g = torch.Generator().manual_seed(seed)
     lens = rng.randint(len_lo, len_hi + 1, size=B)
@@ -311,6 +341,44 @@ def _cpu_generate_sample(n_layers: int, B: int, s0: int, dtype, deadline: float)
     return best_pre, statistics.median(steps[1:] or steps)
 
 
+def _cpu_c1_full(dtype, deadline):
+    """C1 as BASELINE.json states it: the whole step (panorama + navigation forward) through the oracle port with ALL 32
+    decoder layers on the host cores, batch 1.  The 32 layers alias one set of full-width matrices (values do not matter for
+    a timing; 13.5 GB of distinct random weights would only add minutes of initialisation) - every layer still streams and
+    multiplies its own 202 M parameters' worth of data per token."""
+    from oracle import navillm_oracle as O
+    from navillm_b200.tokenizer import SyntheticTokenizer
+    tok = SyntheticTokenizer(base_vocab=VOCAB)
+    prec = "amp_bf16" if dtype == torch.bfloat16 else "fp32"
+    cfg1 = O.OracleConfig(hidden=D_MODEL, n_layers=1, n_heads=N_HEADS, inter=D_FF, vocab=len(tok), image_feat_size=IMG_FEAT, obj_feat_size=768,
+                          cand_id=tok.special["<cand>"], hist_id=tok.special["<hist>"], obj_id=tok.special["<obj>"],
+                          cls_ids=(tok.special["<cls_1>"], tok.special["<cls_2>"]), precision=prec)
+    sd = O.init_state_dict(cfg1, seed=0)
+    for k in list(sd):
+        if k.startswith("lang_model.model.layers.0."):
+            for l in range(1, N_LAYERS):
+                sd[k.replace("layers.0.", f"layers.{l}.")] = sd[k]
+    cfg = O.OracleConfig(**{**cfg1.__dict__, "n_layers": N_LAYERS})
+    host, meta = make_workload(1234, **{k: v for k, v in WORKLOADS["c1"].items() if k not in ("name", "max_length")})
+    times = []
+    with torch.no_grad():
+        for i in range(1 + CPU_MAX_TIMED):
+            t0 = time.perf_counter()
+            pano = O.forward_panorama(sd, cfg, host["view_img_fts"], meta["view_lens"], host["loc_fts"], host["nav_types"])
+            pe = pano["pano_embeds"]
+            nav = {"vp_img_embeds": torch.cat([torch.zeros_like(pe[:, :1]), pe], 1), "pano_masks": torch.ones((1, N_VIEWS + 1), dtype=torch.bool),
+                   "vp_pos_fts": host["vp_pos_fts"], "vp_cand_vpids": meta["vp_cand_vpids"], "gmap_img_embeds": host["gmap_img_embeds"],
+                   "gmap_step_ids": meta["gmap_step_ids"], "gmap_pos_fts": host["gmap_pos_fts"], "gmap_masks": meta["gmap_masks"],
+                   "gmap_visited_masks": meta["gmap_visited_masks"], "gmap_vpids": meta["gmap_vpids"], "hist_vis": [[]], "prompts": meta["prompts"]}
+            O.forward_navigation(sd, cfg, nav, tok)
+            dt = time.perf_counter() - t0
+            times.append(dt)
+            if time.time() + dt > deadline:
+                break
+    timed_ = times[1:] or times
+    return statistics.median(timed_), len(times) - 1
+
+
 def cpu_reference_sample(workload: str, n_layers: int = 2, budget_s: float = CPU_BUDGET_S):
     """Times the oracle port in the reference's own precision ('amp_bf16' -> bf16 LM) AND in fp32 and reports the faster one:
     hosts without AMX / AVX512-BF16 run torch's bf16 CPU GEMMs far below their fp32 rate, and a user of the reference on
@@ -324,28 +392,38 @@ def cpu_reference_sample(workload: str, n_layers: int = 2, budget_s: float = CPU
         if k == 1 and time.time() > t_start + 0.75 * budget_s:
             break                                                    # fp32 used the budget: report fp32 only
         name = "fp32" if dtype == torch.float32 else "bf16"
-        if workload == "c3":
+        if workload == "c1":
+            t, n_timed = _cpu_c1_full(dtype, deadline)
+            res[name] = {"value": 1.0 / t, "detail": f"{t:.2f} s per full 32-layer forward step (median of {max(n_timed, 1)})"}
+        elif workload == "c3":
             pre, stp = _cpu_generate_sample(n_layers, wl["B"], wl["n_cand_tok"] + wl["n_text"], dtype, deadline)
             total = (pre + (wl["n_new"] - 1) * stp) * N_LAYERS / n_layers
             res[name] = {"value": wl["B"] * wl["n_new"] / total, "detail": f"prefill {pre:.2f} s + decode step {stp * 1e3:.0f} ms per {n_layers} layers"}
         else:
-            seq = (wl["len_lo"] + wl["len_hi"]) // 2
+            seq = (wl["len_lo"] + wl["len_hi"]) // 2 if "len_lo" in wl else C4_MEAN_LEN
             t, n_timed = _cpu_train_sample(n_layers, seq, dtype, deadline)
             res[name] = {"value": 1.0 / (t * N_LAYERS / n_layers), "detail": f"{t:.2f} s per pass (median of {max(n_timed, 1)})"}
         log(f"cpu arm {name}: {res[name]['value']:.4g} ({res[name]['detail']})")
     best = max(res, key=lambda k: res[k]["value"])
-    if workload == "c3":
+    if workload == "c1":
+        sample = (f"oracle port ({best}), the WHOLE C1 step on the host cores: panorama encoder + navigation forward with all {N_LAYERS} "
+                  f"full-width Vicuna-7B layers, batch 1, S=192 (no scaling)")
+    elif workload == "c3":
         sample = (f"oracle port ({best}), B={wl['B']}, S0={wl['n_cand_tok'] + wl['n_text']}, {n_layers} of {N_LAYERS} full-width Vicuna-7B "
                   f"layers: prefill + KV-cache decode steps timed, scaled x{N_LAYERS}/{n_layers} to {wl['n_new']} new tokens")
     else:
-        sample = (f"oracle port ({best}), B=1, seq={(wl['len_lo'] + wl['len_hi']) // 2} (workload mean length), {n_layers} of {N_LAYERS} "
+        sample = (f"oracle port ({best}), B=1, seq={(wl['len_lo'] + wl['len_hi']) // 2 if 'len_lo' in wl else C4_MEAN_LEN} (workload mean length), {n_layers} of {N_LAYERS} "
                   f"full-width Vicuna-7B layers fwd+bwd timed, scaled x{N_LAYERS}/{n_layers}")
     sample += " [" + ", ".join(f"{k}: {v['value']:.4g}/s, {v['detail']}" for k, v in res.items()) + "; faster one reported]"
     return {"value": res[best]["value"], "cores": cores, "sample": sample, "wall_s": time.time() - t_start}
 
 
 def metric_of(workload: str):
-    return ("generated_tokens_per_sec", "tokens/s") if workload == "c3" else ("nav_steps_per_sec", "nav-steps/s")
+    if workload == "c3":
+        return ("generated_tokens_per_sec", "tokens/s")
+    if workload == "c4":
+        return ("mixed_samples_per_sec", "samples/s")
+    return ("nav_steps_per_sec", "nav-steps/s")
 
 
 def run_reference_arm(a, rank, world):
@@ -355,7 +433,7 @@ def run_reference_arm(a, rank, world):
     r = cpu_reference_sample(a.workload, a.cpu_layers)
     v = r["value"]
     metric, unit = metric_of(a.workload)
-    per_step = WORKLOADS[a.workload]["B"] * (WORKLOADS[a.workload].get("n_new", 1))
+    per_step = WORKLOADS[a.workload]["B"] * (WORKLOADS[a.workload].get("n_new", 1))   # units of the metric per bench step
     line = {"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": a.gpus, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": 1000.0 * per_step / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic", "config": {"workload": WORKLOADS[a.workload]["name"]},
@@ -430,7 +508,14 @@ def run_train(a, rank, local_rank, world, dev):
     import contextlib
     sync_ctx = (lambda: contextlib.nullcontext()) if (do_sync or world == 1) else model.no_sync
 
+    fwd_only = a.workload == "c1"                          # the plumbing config: one forward step, no gradient
+    if fwd_only:
+        core_model.eval()
+
     def step_resident():
+        if fwd_only:
+            with torch.no_grad():
+                return nav_step(model, resident, meta, dev, text=text)
         core_model.zero_grad(lazy=True)
         with sync_ctx():
             loss = nav_step(model, resident, meta, dev, text=text)
@@ -438,6 +523,9 @@ def run_train(a, rank, local_rank, world, dev):
         return loss
 
     def step_e2e():
+        if fwd_only:
+            with torch.no_grad():
+                return float(nav_step(model, upload(), meta, dev, text=tokenize()))
         core_model.zero_grad(lazy=True)
         d = upload()
         with sync_ctx():
@@ -481,7 +569,7 @@ def run_train(a, rank, local_rank, world, dev):
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None
         # algorithmic FLOPs of the whole step on REAL (non-pad) tokens: 3 x (12.952 GF/token + attention)
         lens = np.asarray(text["attention_mask"].sum(1), dtype=np.float64)
-        algo_step = 3.0 * float((lens * 12.952e9 + 0.262144e6 * lens * lens).sum()) + 3.0 * 2.229e9 * B
+        algo_step = (1.0 if fwd_only else 3.0) * (float((lens * 12.952e9 + 0.262144e6 * lens * lens).sum()) + 2.229e9 * B)
         traffic, traffic_src = gemm_traffic()
         st = core_model.grad_sync.stats
         line = {
@@ -515,6 +603,144 @@ def run_train(a, rank, local_rank, world, dev):
             line["INVALID"] = f"debug run with {a.layers} layers"
         if world > 1 and a.grad_sync == "none":
             line["INVALID"] = "debug run without the gradient exchange"
+        print(json.dumps(line), flush=True)
+        log("done")
+
+
+def run_mixed(a, rank, local_rank, world, dev):
+    """c4: four micro-batches of different task shapes per step, accumulated under no_sync(), one exchange per step."""
+    import contextlib
+    import torch.distributed as dist
+    from navillm_b200 import _lib
+    wl = WORKLOADS["c4"]
+    if a.layers != N_LAYERS:
+        import navillm_b200.nav_model as nm
+        nm.VICUNA_7B["num_hidden_layers"] = a.layers
+    log(f"building the model ({a.layers} layers) on {dev}")
+    core_model = build_model(dev, seed=0)
+    core_model._ensure()
+    model = core_model
+    do_sync = world > 1 and a.grad_sync != "none"
+    if world > 1:
+        from navillm_b200.parallel import DistributedDataParallel as DDP
+        core_model.grad_sync.overlap = a.grad_sync == "overlap"
+        model = DDP(core_model, device_ids=[local_rank], find_unused_parameters=True)
+    MB = 2
+    shapes = [("r2r", dict(B=MB, n_hist=8, n_gmap=24, n_cand=16, len_lo=256, len_hi=512)),
+              ("cvdn", dict(B=MB, n_hist=20, n_gmap=36, n_cand=16, len_lo=512, len_hi=1024)),
+              ("soon", dict(B=MB, n_hist=10, n_gmap=26, n_cand=16, len_lo=384, len_hi=768))]
+    navs = []
+    for k, (name, kw) in enumerate(shapes):
+        host, meta = make_workload(1234 + 10 * rank + k, **kw)
+        navs.append((name, {k2: v.pin_memory() for k2, v in host.items()}, meta, meta["target_cols"].pin_memory()))
+    g = torch.Generator().manual_seed(99 + rank)
+    N_OBJ = 40
+    og_host = {"obj_img_fts": torch.randn(MB, N_OBJ, 768, generator=g).pin_memory(), "obj_loc_fts": torch.randn(MB, N_OBJ, 7, generator=g).pin_memory(),
+               "targets": torch.randint(0, N_OBJ, (MB,), generator=g).pin_memory()}
+    rng = np.random.RandomState(77 + rank)
+    qa_host = {"features": [torch.randn(N_VIEWS, IMG_FEAT, generator=g).pin_memory() for _ in range(MB)]}
+    qa_prompts = ["Scene " + " ".join(["<cand>"] * N_VIEWS) + " Question " + " ".join(f"w{i}" for i in rng.randint(0, 5000, size=290)) + " Answer"
+                  for _ in range(MB)]
+    qa_answers = [[" ".join(f"w{i}" for i in rng.randint(0, 5000, size=15))] for _ in range(MB)]
+    h2d_bytes = sum(v.numel() * v.element_size() for _, p, _, t in navs for v in list(p.values()) + [t]) \
+        + sum(v.numel() * v.element_size() for v in og_host.values()) + sum(f.numel() * 4 for f in qa_host["features"])
+
+    def micro_batches(up):
+        """yields callables, one per micro-batch, each returning its loss"""
+        for name, pinned, meta, tgt in navs:
+            def nav(pinned=pinned, meta=meta, tgt=tgt, name=name):
+                d = {k: up(v) for k, v in pinned.items()}
+                d["target_cols"] = up(tgt)
+                if name != "soon":
+                    return nav_step(model, d, meta, dev)
+                # SOON: the panorama call also projects the objects; the step ends with the object-grounding sub-task
+                B = MB
+                pano = model("panorama", {"view_img_fts": d["view_img_fts"], "view_lens": meta["view_lens"], "loc_fts": d["loc_fts"],
+                                          "nav_types": d["nav_types"], "obj_img_fts": up(og_host["obj_img_fts"]),
+                                          "obj_lens": torch.full((B,), N_OBJ, dtype=torch.long), "obj_loc_fts": up(og_host["obj_loc_fts"])})
+                n_hist = d["hist_vis"].shape[1]
+                og = model("object_grounding", {"data_type": ["soon"] * B, "obj_embeds": pano["obj_embeds"], "obj_masks": pano["obj_masks"],
+                                                "obj_loc_fts": up(og_host["obj_loc_fts"]),
+                                                "hist_vis": [list(d["hist_vis"][b].unbind(0)) for b in range(B)],
+                                                "prompts": ["Find " + " ".join(["<hist>"] * n_hist) + " Objects " + " ".join(["<cand>"] * N_OBJ) + " <cls_1>"
+                                                            for _ in range(B)]})
+                og_loss = torch.nn.functional.cross_entropy(og["obj_logits"].float(), up(og_host["targets"]), reduction="sum") / B
+                return nav_step(model, d, meta, dev) + og_loss
+            yield nav
+
+        def qa():
+            out = model("3dqa", {"question": [""] * MB, "prompts": qa_prompts, "answers": qa_answers,
+                                 "features": [up(f) for f in qa_host["features"]]}, training=True)
+            return out.loss.float()
+        yield qa
+
+    def step(up, read):
+        core_model.zero_grad(lazy=True)
+        mbs = list(micro_batches(up))
+        total = 0.0
+        for i, mb in enumerate(mbs):
+            last = i == len(mbs) - 1
+            ctx = contextlib.nullcontext() if ((last and do_sync) or world == 1) else model.no_sync()
+            with ctx:                                   # tasks/agents/mp3d_agent.py:661-667: only the last backward exchanges
+                loss = mb()
+                loss.backward()
+            if read:
+                total += float(loss.detach())
+        return total
+
+    resident_cache = {}
+
+    def up_resident(v):
+        k = id(v)
+        if k not in resident_cache:
+            resident_cache[k] = v.to(dev)
+        return resident_cache[k]
+
+    up_h2d = lambda v: v.to(dev, non_blocking=True)
+    log(f"warm-up: {a.warmup} steps")
+    for _ in range(a.warmup):
+        step(up_resident, False)
+    torch.cuda.synchronize()
+    launches0 = _lib.launch_count
+    log(f"timed region: {a.steps} steps")
+    with ClockSampler(local_rank) as clk:
+        ms = timed(lambda: step(up_resident, False), a.steps, world, dev)
+    launches = (_lib.launch_count - launches0) // max(a.steps, 1)
+    log(f"timed region done: {ms / a.steps:.1f} ms/step")
+    if a.profile:
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / a.steps, "launches": int(launches)}))
+        return
+    step(up_h2d, True)
+    ms_e2e = timed(lambda: step(up_h2d, True), a.steps, world, dev)
+    log(f"e2e done: {ms_e2e / a.steps:.1f} ms/step")
+    if rank == 0:
+        pk = peaks()
+        B = wl["B"]
+        lens = np.concatenate([m["lens"] for _, _, m, _ in navs] + [np.asarray([1 + N_VIEWS + 290 + 4 + 16] * MB)]).astype(np.float64)
+        lens = np.concatenate([lens, np.asarray([1 + 10 + N_OBJ + 3] * MB, dtype=np.float64)])      # + the object-grounding prompts
+        algo_step = 3.0 * float((lens * 12.952e9 + 0.262144e6 * lens * lens).sum()) + 3.0 * 2.229e9 * (len(navs) * MB + MB)
+        st = core_model.grad_sync.stats
+        line = {"metric": "mixed_samples_per_sec", "value": world * B * a.steps / (ms / 1e3), "unit": "samples/s", "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                "data": "synthetic",
+                "config": {"workload": wl["name"], "layers": a.layers, "l2": "inputs_exceed_l2 (13.5 GB of weights streamed per pass)",
+                           "micro_batches": "r2r | cvdn | soon (+object grounding) | scanqa; no_sync() around all but the last backward",
+                           "grad_exchange": (f"one exchange per step; {st['collectives']} collectives in {st['exchanges']} exchanges so far; "
+                                             + ("NVLS in-switch all-reduce" if getattr(model, "nvls", False) else "NCCL")) if world > 1 else "n/a"},
+                "e2e": {"value": world * B * a.steps / (ms_e2e / 1e3), "unit": "samples/s", "h2d_bytes_per_step": int(h2d_bytes),
+                        "d2h_bytes_per_step": 4 * 4, "ms_per_step": ms_e2e / a.steps},
+                "gpu_launches": int(launches),
+                "roofline": {"bound": "tensor", "kernel": "whole step (algorithmic FLOPs of the four micro-batches on real tokens)",
+                             "achieved": algo_step / 1e12 / (ms / a.steps / 1e3), "peak": pk["bf16_tflops"], "unit": "TFLOP/s",
+                             "frac": algo_step / 1e12 / (ms / a.steps / 1e3) / pk["bf16_tflops"], "peak_src": pk["src"] + " (sustained cuBLAS bf16)",
+                             "step_algorithmic_tflop": algo_step / 1e12, "traffic": None},
+                "clocks": clk.summary()}
+        if not a.no_cpu_baseline and world == 1:
+            r = cpu_reference_sample("c4", a.cpu_layers)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "samples/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+        if a.layers != N_LAYERS:
+            line["INVALID"] = f"debug run with {a.layers} layers"
         print(json.dumps(line), flush=True)
         log("done")
 
@@ -605,7 +831,8 @@ def run_generate(a, rank, local_rank, world, dev):
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "decode step (CUDA graph: gemm_skinny_tcgen05 x4/layer + rmsnorm/rope-kv/decode_attn)", "achieved": achieved,
                          "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": (achieved / pk["hbm_gbs"]) if achieved else None, "peak_src": pk["src"],
-                         "algorithmic_bytes_per_token_step": bytes_tok, "traffic": None},
+                         "algorithmic_bytes_per_token_step": bytes_tok, "traffic": decode_traffic(a.layers)[0],
+                         "traffic_unit": "bytes per decode step (DRAM read+write)", "traffic_src": decode_traffic(a.layers)[1]},
             "clocks": clk.summary(),
         }
         if not a.no_cpu_baseline and world == 1:
@@ -652,6 +879,8 @@ def main():
     try:
         if a.workload == "c3":
             run_generate(a, rank, local_rank, world, dev)
+        elif a.workload == "c4":
+            run_mixed(a, rank, local_rank, world, dev)
         else:
             run_train(a, rank, local_rank, world, dev)
     finally:
