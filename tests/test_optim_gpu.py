@@ -55,3 +55,47 @@ def test_flat_adamw_matches_torch(cuda_dev):
             assert e_mine <= e_ref + 2.0 ** -8 * t32.abs().max().item(), (e_mine, e_ref)
     sd = opt.state_dict()
     assert len(sd["state"]) == len(params) and sd["state"][0]["exp_avg"].shape == params[0].shape
+
+
+def test_optimizer_state_interop_with_torch_adamw_indexing(cuda_dev):
+    """State written by torch.optim.AdamW over ``model.parameters()`` (what the reference saves, tools/optims.py:43,69-71)
+    loads by index; a state dict whose per-index shapes do not match this model's parameter order (e.g. written with
+    up_proj / down_proj swapped) is rejected with a clear error instead of being copied or silently mis-assigned; a lazy
+    zero_grad followed by an optimizer step with NO backward in between applies zero gradients, not stale ones."""
+    from navillm_b200.optim import FlatAdamW
+    from tests.test_navmodel_gpu import build_model
+    g = torch.load(GOLD / "nav_amp_bf16.pt", weights_only=False)
+    model, _ = build_model(g, cuda_dev)
+    model._ensure()
+    params = [p for p in model.parameters() if p.requires_grad]
+    # a torch AdamW over the same parameter list, one step -> its state dict uses parameter INDICES
+    for p in params:
+        p.grad.copy_(torch.ones_like(p) * 0.01)
+    topt = torch.optim.AdamW(params, lr=0.0)
+    topt.step()
+    tsd = topt.state_dict()
+    opt = FlatAdamW(model, lr=1e-3)
+    opt.load_state_dict(tsd)
+    back = opt.state_dict()
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    for i in (0, names.index("lang_model.model.layers.0.mlp.down_proj.weight"), names.index("lang_model.model.layers.0.mlp.up_proj.weight"), len(params) - 1):
+        assert torch.equal(back["state"][i]["exp_avg"].cpu(), tsd["state"][i]["exp_avg"].cpu()), names[i]
+    # swapped down/up entries (the order of an implementation that registers gate, up, down): rejected
+    i_dn, i_up = names.index("lang_model.model.layers.0.mlp.down_proj.weight"), names.index("lang_model.model.layers.0.mlp.up_proj.weight")
+    assert i_dn < i_up                                   # reference order: gate_proj, down_proj, up_proj (transformers 4.28)
+    if params[i_dn].shape != params[i_up].shape:
+        bad = {"state": dict(tsd["state"]), "param_groups": tsd["param_groups"]}
+        bad["state"][i_dn], bad["state"][i_up] = tsd["state"][i_up], tsd["state"][i_dn]
+        with pytest.raises(ValueError):
+            opt.load_state_dict(bad)
+    with pytest.raises(ValueError):
+        opt.load_state_dict({"state": {}, "param_groups": [{"params": list(range(len(params) + 1))}]})
+    # lazy zero + step without a backward: per-layer gradients count as zero
+    q = model.lang_model.model.layers[0].self_attn.q_proj.weight
+    q.grad.fill_(5.0)
+    model.zero_grad(lazy=True)
+    opt2 = FlatAdamW(model, lr=1e-2, weight_decay=0.0)
+    before = q.detach().float().clone()
+    opt2.step(max_grad_norm=40.0)
+    torch.cuda.synchronize()
+    assert float(q.grad.float().abs().max()) == 0.0 and torch.equal(q.detach().float(), before)
