@@ -13,6 +13,8 @@
 // shared memory in the leader CTA - no atomics, no workspace, no second kernel.  4-stage rings of 18 KB let three
 // CTAs share an SM, so a 4096-column projection runs as 256 CTAs (S = 8) instead of 32.
 //   warp 0  TMA producer   warp 1  tcgen05.mma issuer   warps 2..5  epilogue (TMEM -> DSMEM reduce -> bf16 (+addend))
+#include <stdlib.h>
+
 #include "nv_common.cuh"
 #include "nv_host.h"
 
@@ -236,7 +238,15 @@ static int skinny_launch(const void* X, int64_t ldx, const void* W, int64_t ldw,
   const uint32_t tiles = ceil_div_u32(N, swiglu_f ? 64 : SK_BN), total_kb = ceil_div_u32(K, SK_BK);
   // largest power-of-two split (cluster size <= 8) that keeps about three CTAs per SM and >= 8 k-blocks per CTA
   uint32_t splits = 1;
-  while (splits < 8 && tiles * splits * 2 <= 3u * (uint32_t)sm_count() && total_kb / (splits * 2) >= 8) splits *= 2;
+  static int max_splits = -1, min_kb = -1;
+  if (max_splits < 0) {                                    // developer knobs for tools/skinny_bench.py sweeps
+    const char* e = getenv("NV_SKINNY_MAX_SPLITS");
+    max_splits = (e && atoi(e) > 0) ? atoi(e) : 8;
+    const char* f = getenv("NV_SKINNY_MIN_KB");
+    min_kb = (f && atoi(f) > 0) ? atoi(f) : 8;
+  }
+  while (splits < (uint32_t)max_splits && tiles * splits * 2 <= 3u * (uint32_t)sm_count() && total_kb / (splits * 2) >= (uint32_t)min_kb)
+    splits *= 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(tiles * splits);
   cfg.blockDim = dim3(SK_THREADS);
