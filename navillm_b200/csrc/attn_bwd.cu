@@ -391,14 +391,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 // dk/dv pass (transposed scores: TMEM lanes = keys)
 // ======================================================================================================
 struct DkvSmem {
-  static constexpr uint32_t NST = 3;
+  static constexpr uint32_t NST = 4;                              // 3 stages left 2 sub-blocks of slack < TMA latency (trace); 5 do not fit next to the 2 KB of static smem
   static constexpr uint32_t K_OFF = 0, V_OFF = AB_T128;
   static constexpr uint32_t QO_OFF = 2 * AB_T128;                 // NST x (Q 16K | dO 16K)
   static constexpr uint32_t BAR_OFF = QO_OFF + NST * 2 * AB_T64;
-  // res_full, qo_full[3], qo_empty[3], sdp_full[2], sdp_empty[2], pds_full[2], done
-  static constexpr uint32_t NUM_BARS = 14;
+  // res_full, qo_full[NST], qo_empty[NST] (slots for 5), sdp_full[2], sdp_empty[2], pds_full[2], done
+  static constexpr uint32_t NUM_BARS = 18;
   static constexpr uint32_t DYN_BYTES = BAR_OFF + NUM_BARS * 8 + 16 + 1024;
 };
+static_assert(DkvSmem::DYN_BYTES + 2048 <= 232448, "dk/dv pass shared memory (dynamic + s_stats)");
 
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_k,
@@ -415,12 +416,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   uint8_t* sQO = smem + L::QO_OFF;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
   uint64_t* res_full = bars + 0;
-  uint64_t* qo_full = bars + 1;     // [3]
-  uint64_t* qo_empty = bars + 4;    // [3]
-  uint64_t* sdp_full = bars + 7;    // [2]
-  uint64_t* sdp_empty = bars + 9;   // [2]
-  uint64_t* pds_full = bars + 11;   // [2] P^T(n) / dS^T(n) are in TMEM (over S^T[b] / dP^T[b])
-  uint64_t* done = bars + 13;
+  uint64_t* qo_full = bars + 1;     // [5]
+  uint64_t* qo_empty = bars + 6;    // [5]
+  uint64_t* sdp_full = bars + 11;   // [2]
+  uint64_t* sdp_empty = bars + 13;  // [2]
+  uint64_t* pds_full = bars + 15;   // [2] P^T(n) / dS^T(n) are in TMEM (over S^T[b] / dP^T[b])
+  uint64_t* done = bars + 17;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + L::NUM_BARS);
   __shared__ float s_stats[8][2][32];   // per compute warp: LSE*log2e and D of its 32 query columns
 
@@ -443,7 +444,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_k); tma_prefetch_desc(&tmap_v); tma_prefetch_desc(&tmap_do);
     mbar_init(res_full, 1);
-    for (int i = 0; i < 3; ++i) { mbar_init(&qo_full[i], 1); mbar_init(&qo_empty[i], 1); }
+    for (uint32_t i = 0; i < L::NST; ++i) { mbar_init(&qo_full[i], 1); mbar_init(&qo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&sdp_full[i], 1); mbar_init(&sdp_empty[i], 8); }
     mbar_init(&pds_full[0], 8); mbar_init(&pds_full[1], 8);
     mbar_init(done, 1);
@@ -466,7 +467,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
     __syncwarp();
     for (uint32_t n = 0; n < n_it; ++n) {
-      const uint32_t st = n % 3, use = n / 3;
+      const uint32_t st = n % L::NST, use = n / L::NST;
       mbar_wait(&qo_empty[st], (use & 1) ^ 1);
       if (elect_one()) {
         mbar_arrive_expect_tx(&qo_full[st], 2 * AB_T64);
@@ -482,8 +483,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     const uint64_t k_k = umma_smem_desc_sw128(smem_u32(sK), 0, 1024);
     const uint64_t v_k = umma_smem_desc_sw128(smem_u32(sV), 0, 1024);
     auto issue_sdp = [&](uint32_t n) {
-      const uint32_t st = n % 3, b = n & 1;
-      mbar_wait(&qo_full[st], (n / 3) & 1);
+      const uint32_t st = n % L::NST, b = n & 1;
+      mbar_wait(&qo_full[st], (n / L::NST) & 1);
       mbar_wait(&sdp_empty[b], ((n >> 1) & 1) ^ 1);
       tc_fence_after();
       if (elect_one()) {
@@ -511,7 +512,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     issue_sdp(0);
     for (uint32_t n = 0; n < n_it; ++n) {
       if (n + 1 < n_it) issue_sdp(n + 1);
-      const uint32_t st = n % 3, b = n & 1;
+      const uint32_t st = n % L::NST, b = n & 1;
       mbar_wait(&pds_full[b], (n >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {

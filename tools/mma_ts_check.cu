@@ -12,14 +12,6 @@
 
 using namespace nv;
 
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 // deterministic small integers: exact products / sums in bf16 x bf16 -> fp32
 __device__ __forceinline__ float aval(uint32_t m, uint32_t k) { return (float)((int)((m * 7 + k * 13) % 9) - 4); }
@@ -86,7 +78,9 @@ __global__ void __launch_bounds__(192, 1) ts_kernel(float* out_ss, float* out_ts
       t0 = clock64();
       for (int it = 0; it < iters; ++it)
 #pragma unroll
-        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ts(tD_ts, tA + ks * 8, bd + ks * 2, idesc, 1u);
+        for (uint32_t ks = 0; ks < 4; ++ks) umma_f16_ts(tmem + 384, tA + ks * 8, bd + ks * 2, idesc, 1u);   // scratch D: the
+      // compute warps are reading tD_ts at this moment (round 1 accumulated the rate loop INTO tD_ts and reported the layout
+      // as wrong: that was this race, not the layout - the probes below and the backward kernels confirm it)
       umma_commit(&bar[1]);
     }
     __syncwarp();
