@@ -183,6 +183,9 @@ int nv_kv_store_suffix(const void* qkv, int64_t ld, const int* cu_seqlens, const
                        int B, int T, int Smax, int HD, void* stream);
 int nv_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* vcache, const int* lens, void* out,
                    int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream);
+/* nv_decode_rope_kv + nv_decode_attn in one launch (qkv pre-RoPE, not modified; k / v appended at row lens[b]). */
+int nv_decode_attn_rope(const void* qkv, int64_t ld, const int* lens, const void* cos_t, const void* sin_t, void* kcache,
+                        void* vcache, void* out, int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream);
 int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id,
                      int pad_id, int stop_on_eos, int* next, int B, void* stream);
 int nv_add_int(int* x, int n, int delta, void* stream);

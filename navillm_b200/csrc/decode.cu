@@ -105,13 +105,19 @@ __global__ void decode_rope_kv_kernel(__nv_bfloat16* __restrict__ qkv, int64_t l
 // CTA = (b, h), DA_WARPS warps; half-warps stream keys with 16-byte loads; per-warp online softmax, merged in smem.
 // (8 warps: 256 (b, h) CTAs of 4 warps kept too few loads in flight for a 50 MB cache read; all CTAs are co-resident.)
 constexpr int DA_WARPS = 8;
+// ROPE = true fuses decode_rope_kv_kernel: q points at the PRE-RoPE fused qkv row block [B, 3*H*128]; warp 0 rotates this
+// head's q and k at position lens[b] (same rounding points as rope_kernel), appends the rotated k and the v to the caches
+// and hands the rotated q to the CTA through shared memory - one launch less per decoder layer and token.
+template <bool ROPE>
 __global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(const __nv_bfloat16* __restrict__ q, int64_t ldq,
-                                                          const __nv_bfloat16* __restrict__ kc,
-                                                          const __nv_bfloat16* __restrict__ vc,
+                                                          __nv_bfloat16* __restrict__ kc, __nv_bfloat16* __restrict__ vc,
                                                           const int* __restrict__ lens, __nv_bfloat16* __restrict__ out,
-                                                          int64_t ldo, int Smax, int H, float scale) {
+                                                          int64_t ldo, int Smax, int H, float scale,
+                                                          const __nv_bfloat16* __restrict__ cos_t,
+                                                          const __nv_bfloat16* __restrict__ sin_t) {
   __shared__ float s_m[DA_WARPS], s_l[DA_WARPS];
   __shared__ float s_acc[DA_WARPS][128];
+  __shared__ uint4 s_q[16];                            // rotated q of this head (bf16 x 128)
   griddep_launch();
   griddep_wait();
   const int b = blockIdx.x / H, h = blockIdx.x % H;
@@ -119,8 +125,47 @@ __global__ void __launch_bounds__(DA_WARPS * 32) decode_attn_kernel(const __nv_b
   const int half = lane >> 4, hl = lane & 15;          // half-warp id, lane within the half (8 dims each)
   const int n = lens[b] + 1;                            // keys visible to the new token
   const int HD = H * 128;
+  if (ROPE) {
+    const int p = n - 1;
+    if (w == 0) {
+      if (lane < 16) {                                  // lanes 0..7: q chunk c, lanes 8..15: k chunk c
+        const int c = lane & 7, is_k = lane >> 3;
+        const __nv_bfloat16* base = q + (int64_t)b * ldq + (is_k ? HD : 0) + h * 128;
+        float x1[8], x2[8], c1[8], s1[8], c2[8], s2[8];
+        unpack8d(*reinterpret_cast<const uint4*>(base + c * 8), x1);
+        unpack8d(*reinterpret_cast<const uint4*>(base + 64 + c * 8), x2);
+        unpack8d(*reinterpret_cast<const uint4*>(cos_t + (int64_t)p * 128 + c * 8), c1);
+        unpack8d(*reinterpret_cast<const uint4*>(sin_t + (int64_t)p * 128 + c * 8), s1);
+        unpack8d(*reinterpret_cast<const uint4*>(cos_t + (int64_t)p * 128 + 64 + c * 8), c2);
+        unpack8d(*reinterpret_cast<const uint4*>(sin_t + (int64_t)p * 128 + 64 + c * 8), s2);
+        uint4 o1, o2;
+        uint32_t* q1 = &o1.x; uint32_t* q2 = &o2.x;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          const float a0 = bf16_round(x1[j] * c1[j]) + bf16_round(-x2[j] * s1[j]);
+          const float a1 = bf16_round(x1[j + 1] * c1[j + 1]) + bf16_round(-x2[j + 1] * s1[j + 1]);
+          const float b0 = bf16_round(x2[j] * c2[j]) + bf16_round(x1[j] * s2[j]);
+          const float b1 = bf16_round(x2[j + 1] * c2[j + 1]) + bf16_round(x1[j + 1] * s2[j + 1]);
+          q1[j >> 1] = pack_bf16x2(a0, a1);
+          q2[j >> 1] = pack_bf16x2(b0, b1);
+        }
+        if (!is_k) {
+          s_q[c] = o1; s_q[8 + c] = o2;
+        } else if (p < Smax) {
+          __nv_bfloat16* dst = kc + ((int64_t)b * Smax + p) * HD + h * 128;
+          *reinterpret_cast<uint4*>(dst + c * 8) = o1;
+          *reinterpret_cast<uint4*>(dst + 64 + c * 8) = o2;
+        }
+      } else if (p < Smax) {                            // lanes 16..31: this head's v (16 x 16 bytes)
+        const int v = lane - 16;
+        *reinterpret_cast<uint4*>(vc + ((int64_t)b * Smax + p) * HD + h * 128 + v * 8) =
+            *reinterpret_cast<const uint4*>(q + (int64_t)b * ldq + 2 * HD + h * 128 + v * 8);
+      }
+    }
+    __syncthreads();                                    // rotated q in smem, new k / v rows visible to the whole CTA
+  }
   float qf[8];
-  unpack8d(*reinterpret_cast<const uint4*>(q + (int64_t)b * ldq + h * 128 + hl * 8), qf);
+  unpack8d(ROPE ? s_q[hl] : *reinterpret_cast<const uint4*>(q + (int64_t)b * ldq + h * 128 + hl * 8), qf);
   const float sl2 = scale * 1.4426950408889634f;
   float m = -INFINITY, l = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   // A warp takes 8 consecutive keys per iteration (4 per half-warp): eight 16-byte loads per lane are in flight
@@ -353,8 +398,21 @@ int nv_decode_attn(const void* q, int64_t ldq, const void* kcache, const void* v
                    int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream) {
   NV_REQUIRE(head_dim == 128, "nv_decode_attn: head_dim must be 128");
   if (B == 0) return NV_OK;
-  NV_CUDA(launch_pdl(decode_attn_kernel, dim3(B * H), dim3(DA_WARPS * 32), 0, S_(stream), CBF(q), ldq, CBF(kcache), CBF(vcache), lens, BF(out), ldo,
-                     Smax, H, scale));
+  NV_CUDA(launch_pdl(decode_attn_kernel<false>, dim3(B * H), dim3(DA_WARPS * 32), 0, S_(stream), CBF(q), ldq,
+                     const_cast<__nv_bfloat16*>(CBF(kcache)), const_cast<__nv_bfloat16*>(CBF(vcache)), lens, BF(out), ldo, Smax, H, scale,
+                     (const __nv_bfloat16*)nullptr, (const __nv_bfloat16*)nullptr));
+  return NV_OK;
+}
+
+// Fused form of nv_decode_rope_kv + nv_decode_attn for one new token per sequence: qkv [B, 3*H*128] PRE-RoPE (q | k | v
+// column blocks); rotates q and k at position lens[b], appends k / v to the caches at row lens[b] and attends over rows
+// 0..lens[b].  qkv is not modified.
+int nv_decode_attn_rope(const void* qkv, int64_t ld, const int* lens, const void* cos_t, const void* sin_t, void* kcache,
+                        void* vcache, void* out, int64_t ldo, int B, int Smax, int H, int head_dim, float scale, void* stream) {
+  NV_REQUIRE(head_dim == 128 && (ld & 7) == 0, "nv_decode_attn_rope: head_dim must be 128, ld %% 8 == 0");
+  if (B == 0) return NV_OK;
+  NV_CUDA(launch_pdl(decode_attn_kernel<true>, dim3(B * H), dim3(DA_WARPS * 32), 0, S_(stream), CBF(qkv), ld, BF(kcache), BF(vcache), lens,
+                     BF(out), ldo, Smax, H, scale, CBF(cos_t), CBF(sin_t)));
   return NV_OK;
 }
 

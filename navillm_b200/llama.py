@@ -27,6 +27,8 @@ from . import ops
 # decode GEMMs: 0 = swap-AB skinny kernel for batches <= 16 (csrc/gemm_skinny.cu, default); 128 / 32 = column-tile
 # width of the general kernel (always used for 16 < batch <= 128)
 DECODE_BLOCK_N = int(os.environ.get("NAVILLM_DECODE_BLOCK_N", "0"))
+# weight-gradient GEMMs on a side stream (see LlamaCore.backward)
+WGRAD_STREAM = os.environ.get("NAVILLM_WGRAD_STREAM", "0") != "0"
 
 bf16 = torch.bfloat16
 
@@ -377,6 +379,26 @@ class LlamaCore:
         def add(g):
             return g if acc else None
 
+        # Weight-gradient GEMMs on a SIDE stream (NAVILLM_WGRAD_STREAM=1): nothing downstream in the backward reads a weight
+        # gradient, so they can trail the dgrad chain.  Both streams run persistent CTA-pair GEMMs with dynamic tile claims:
+        # when one kernel's last, partially filled wave leaves CTA pairs idle (o_proj wgrad: 256 pair tiles on 74 pairs = 3.46
+        # waves), the other stream's kernel takes them.
+        side = WGRAD_STREAM and dx.shape[0] >= 1024
+        main = torch.cuda.current_stream() if side else None
+        ws = self._wgrad_stream() if side else None
+
+        def wgrad(a, b, out, *, keep=()):
+            if not side:
+                ops.gemm(a, b, a_mn=True, b_mn=True, out=out, addend=add(out))
+                return
+            ev = torch.cuda.Event()
+            ev.record(main)
+            ws.wait_event(ev)
+            for t in (a, b) + tuple(keep):
+                t.record_stream(ws)                      # the caching allocator must not recycle them under the side stream
+            with torch.cuda.stream(ws):
+                ops.gemm(a, b, a_mn=True, b_mn=True, out=out, addend=add(out))
+
         for l in range(d.n_layers - 1, -1, -1):
             lyr, s = self.model.layers[l], saved[l]
             # ---- MLP:  x_out = xm + down(swiglu(gate_up(rmsnorm2(xm)))) ----
@@ -386,9 +408,9 @@ class LlamaCore:
                 dh = ops.gemm(dx, self.wd[l], b_mn=True)                               # [T,F]  dgrad
                 dgu = ops.swiglu_bwd(s.gu, dh)
                 del dh
-            ops.gemm(dx, s.h, a_mn=True, b_mn=True, out=self.gd[l], addend=add(self.gd[l]))  # dWd += dx^T h
+            wgrad(dx, s.h, self.gd[l])                                                 # dWd += dx^T h
             dxn2 = ops.gemm(dgu, self.wgu[l], b_mn=True)                               # [T,D]
-            ops.gemm(dgu, s.xn2, a_mn=True, b_mn=True, out=self.ggu[l], addend=add(self.ggu[l]))
+            wgrad(dgu, s.xn2, self.ggu[l])
             del dgu
             dxm = ops.rmsnorm_bwd(s.xm, lyr.post_attention_layernorm.weight.data, s.rstd2, dxn2, dres=dx,
                                   dw=lyr.post_attention_layernorm.weight.grad, accumulate_dw=acc)
@@ -400,10 +422,10 @@ class LlamaCore:
             else:
                 dao = ops.gemm(dxm, self.wo[l], b_mn=True)
             if s.rows is None:
-                ops.gemm(dxm, s.ao, a_mn=True, b_mn=True, out=self.go[l], addend=add(self.go[l]))
+                wgrad(dxm, s.ao, self.go[l])
             else:
                 # pruned last layer: everything above ran on the R requested rows; scatter back to [T, D]
-                ops.gemm(dxm, s.ao_r, a_mn=True, b_mn=True, out=self.go[l], addend=add(self.go[l]))
+                wgrad(dxm, s.ao_r, self.go[l])
                 full = torch.zeros_like(s.ao)
                 ops.scatter_rows_(dao, s.rows, full)
                 dao = full
@@ -414,16 +436,29 @@ class LlamaCore:
             dqkv = ops.attn_bwd(s.qkv, s.ao, dao, s.lse, cu, seqlens, H, rope=(pos, self.cos, self.sin), dvec=dvec)
             del dao
             dxn = ops.gemm(dqkv, self.wqkv[l], b_mn=True)
-            ops.gemm(dqkv, s.xn, a_mn=True, b_mn=True, out=self.gqkv[l], addend=add(self.gqkv[l]))
+            wgrad(dqkv, s.xn, self.gqkv[l])
             del dqkv
             dx = ops.rmsnorm_bwd(s.x, lyr.input_layernorm.weight.data, s.rstd1, dxn, dres=dxm,
                                  dw=lyr.input_layernorm.weight.grad, accumulate_dw=acc)
             del dxn, dxm
             saved[l] = None
             if layer_done is not None:
+                if side:                                   # the layer's gradients are complete only when the side stream is
+                    ev = torch.cuda.Event()
+                    ev.record(ws)
+                    main.wait_event(ev)
                 layer_done(l)
+        if side:
+            ev = torch.cuda.Event()
+            ev.record(ws)
+            main.wait_event(ev)                            # whoever reads the gradients next is ordered after the wgrads
         self.flat.overwrite_layer_grads = False
         return dx
+
+    def _wgrad_stream(self):
+        if getattr(self, "_ws", None) is None:
+            self._ws = torch.cuda.Stream()
+        return self._ws
 
 
     # -------------------------------------------------------------------------------------------------
@@ -448,11 +483,11 @@ class LlamaCore:
             xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
             qkv = lin(xn, self.wqkv[l])
             if d.head_dim == 128:
-                ops.decode_rope_kv_(qkv, lens, self.cos, self.sin, kc[l], vc[l], H)     # RoPE + cache append in one launch
+                ao = ops.decode_attn_rope(qkv, lens, self.cos, self.sin, kc[l], vc[l], H)   # RoPE + cache append + attention
             else:
                 ops.rope_(qkv, lens, self.cos, self.sin, 2 * H, d.head_dim)
                 ops.kv_append(qkv, lens, kc[l], vc[l])
-            ao = ops.decode_attn(qkv, kc[l], vc[l], lens, H)
+                ao = ops.decode_attn(qkv, kc[l], vc[l], lens, H)
             xm = lin(ao, self.wo[l], x)
             xn2, _ = ops.rmsnorm_fwd(xm, lyr.post_attention_layernorm.weight.data, d.rms_eps)
             if fuse_mlp:

@@ -517,6 +517,20 @@ def decode_attn(q, kc, vc, lens, n_heads, *, out=None, scale=None):
     return out
 
 
+def decode_attn_rope(qkv, lens, cos_t, sin_t, kc, vc, n_heads, *, out=None, scale=None):
+    """decode_rope_kv_ + decode_attn in ONE launch: qkv [B, 3*H*128] bf16 PRE-RoPE (not modified), lens int32 [B] = position of
+    the new token; the rotated k and the v are appended to the caches at row lens[b].  Returns [B, H*128] bf16."""
+    B, Smax, HD = kc.shape
+    if out is None:
+        out = torch.empty((B, HD), dtype=bf16, device=qkv.device)
+    if scale is None:
+        scale = 128 ** -0.5
+    check(_lib.load().nv_decode_attn_rope(ptr(qkv), i64(qkv.stride(0)), ptr(lens), ptr(cos_t), ptr(sin_t), ptr(kc), ptr(vc), ptr(out),
+                                          i64(out.stride(0)), i32(B), i32(Smax), i32(n_heads), i32(128), f32(scale), stream_ptr()),
+          "nv_decode_attn_rope")
+    return out
+
+
 def argmax_masked(logits, special, finished, eos_id, pad_id, stop_on_eos, next_ids):
     B, V = logits.shape
     check(_lib.load().nv_argmax_masked(ptr(logits), i64(logits.stride(0)), i32(V), ptr(special), i32(special.numel()),

@@ -176,3 +176,26 @@ def test_decode_rope_kv_matches_rope_then_append(cuda_dev):
     ops.kv_append(b, lens, kc2, vc2)
     torch.cuda.synchronize()
     assert torch.equal(a, b) and torch.equal(kc, kc2) and torch.equal(vc, vc2)
+
+
+def test_decode_attn_rope_fused_matches_two_kernels(cuda_dev):
+    """nv_decode_attn_rope (RoPE + cache append + attention in one launch) is bit-identical to nv_decode_rope_kv followed by
+    nv_decode_attn: outputs, appended cache rows, untouched cache rows; the input qkv is not modified."""
+    from navillm_b200 import ops
+    from navillm_b200.llama import LlamaDims, rope_tables
+    B, H, Smax = 5, 4, 192
+    HD = H * 128
+    g = torch.Generator(device="cpu").manual_seed(1)
+    qkv = torch.randn(B, 3 * HD, generator=g).to(cuda_dev, torch.bfloat16)
+    lens = torch.tensor([0, 3, 17, 190, 100], dtype=torch.int32, device=cuda_dev)
+    cos, sin = rope_tables(LlamaDims(hidden=HD, n_layers=1, n_heads=H, inter=256, vocab=64), cuda_dev)
+    kc = (torch.randn(B, Smax, HD, generator=g) * 0.5).to(cuda_dev, torch.bfloat16)
+    vc = (torch.randn(B, Smax, HD, generator=g) * 0.5).to(cuda_dev, torch.bfloat16)
+    kc2, vc2, q2 = kc.clone(), vc.clone(), qkv.clone()
+    ops.decode_rope_kv_(q2, lens, cos, sin, kc2, vc2, H)
+    want = ops.decode_attn(q2, kc2, vc2, lens, H)
+    q1 = qkv.clone()
+    got = ops.decode_attn_rope(q1, lens, cos, sin, kc, vc, H)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert torch.equal(kc, kc2) and torch.equal(vc, vc2) and torch.equal(q1, qkv)
