@@ -236,6 +236,7 @@ class _LMFn(torch.autograd.Function):
             dy = ops.gemm(dlogits, lm.lm_head.weight.data, b_mn=True)                    # [Nl, D]
             ops.gemm(dlogits, hn, a_mn=True, b_mn=True, out=lm.lm_head.weight.grad, addend=lm.lm_head.weight.grad)
         dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)                     # [R, D]: gradient at the requested rows
+        lm.grad_sync.short_backward = pp.T < lm.SHORT_BACKWARD_TOKENS
         dx = core.backward(dg, ctx.tape, layer_done=lm._grad_sync_hook())
         ops.embed_bwd_weight_(dx, pp.ids, lm.model.embed_tokens.weight.grad)
         dvis = ops.embed_bwd_vis(dx, pp.vis_src, ctx.n_vis) if ctx.has_vis else None
@@ -353,6 +354,8 @@ class ModifiedLlamaForCausalLM(nn.Module):
         flat, layers = self.flat, self.model.layers
         starts = [flat.offset_of(l.self_attn.q_proj.weight) for l in layers] + [flat.offset_of(self.model.embed_tokens.weight)]
         return self.grad_sync.layer_hook(flat, starts, self.dims.n_layers)
+
+    SHORT_BACKWARD_TOKENS = 4096     # below this many packed rows a backward is shorter than the exchange of its gradients
 
     def _clean_grad_segments(self):
         """Flat-gradient ranges known to be all-zero (see GradSync.exchange): lm_head after a zero_grad when no LM-loss

@@ -55,7 +55,11 @@ class NvlsReducer:
     def __init__(self, ctas: int = 0):
         self.stream = torch.cuda.Stream()
         self.handles = {}
+        # CTAs issuing the multimem operations: few while the reduction hides behind the backward (they share SMs with the
+        # persistent GEMMs; 8 vs 32 CTAs: 366.7 vs 368.9 ms/step at 8 GPUs), many when it is exposed anyway (the tail after the
+        # backward, or a backward too short to hide 13.5 GB behind: 8 CTAs move 214 GB/s per rank pair)
         self.ctas = ctas or int(os.environ.get("NAVILLM_NVLS_CTAS", "8"))
+        self.ctas_exposed = max(self.ctas, int(os.environ.get("NAVILLM_NVLS_CTAS_EXPOSED", "32")))
         self.n_reduced = 0
 
     @staticmethod
@@ -77,7 +81,7 @@ class NvlsReducer:
     def has(self, flat) -> bool:
         return id(flat) in self.handles
 
-    def all_reduce(self, flat, a: int, b: int, scale: float):
+    def all_reduce(self, flat, a: int, b: int, scale: float, exposed: bool = False):
         from . import _lib
         hdl, buf = self.handles[id(flat)]
         if flat.flat_grad.data_ptr() != buf.data_ptr():
@@ -90,7 +94,7 @@ class NvlsReducer:
             hdl.barrier(channel=0)
             _lib.check(_lib.load().nv_multimem_allreduce(_lib.ctypes.c_uint64(int(hdl.multicast_ptr)), _lib.i64(a), _lib.i64(b - a),
                                                          _lib.i32(1 if flat.dtype == torch.bfloat16 else 0), _lib.i32(hdl.rank),
-                                                         _lib.i32(hdl.world_size), _lib.f32(scale), _lib.i32(self.ctas),
+                                                         _lib.i32(hdl.world_size), _lib.f32(scale), _lib.i32(self.ctas_exposed if exposed else self.ctas),
                                                          _lib.ctypes.c_void_p(self.stream.cuda_stream)), "nv_multimem_allreduce")
             hdl.barrier(channel=0)
             done = torch.cuda.Event()
@@ -111,6 +115,7 @@ class GradSync:
         self._pending: List[tuple] = []
         self._lm_layers_reduced = False
         self.reducer: Optional[NvlsReducer] = None            # set by the DDP wrapper when NVLS multicast is available
+        self.short_backward = False   # set per pass by the LM: too few tokens to hide the exchange behind (see NvlsReducer)
         self.stats = {"collectives": 0, "exchanges": 0, "async_slices": 0}
 
     # ---- forward side -------------------------------------------------------------------------------------------
@@ -149,7 +154,7 @@ class GradSync:
             if l not in ends:
                 return
             if nvls is not None:                                  # in-switch reduction on the side stream
-                self._pending.append((nvls.all_reduce(flat, starts[l], starts[ends[l]], 1.0 / ws), None, ws))
+                self._pending.append((nvls.all_reduce(flat, starts[l], starts[ends[l]], 1.0 / ws, exposed=self.short_backward), None, ws))
             else:
                 sl = flat.flat_grad[starts[l]:starts[ends[l]]]
                 h = dist.all_reduce(sl, op=avg, async_op=True)
@@ -206,7 +211,7 @@ class GradSync:
                 ranges.append((cur, hi))
             for a, b in ranges:
                 if self.reducer is not None and self.reducer.has(flat):
-                    self._pending.append((self.reducer.all_reduce(flat, a, b, 1.0 / ws), None, ws))
+                    self._pending.append((self.reducer.all_reduce(flat, a, b, 1.0 / ws, exposed=True), None, ws))
                 else:
                     buf = flat.flat_grad[a:b]
                     dist.all_reduce(buf, op=avg)
