@@ -25,9 +25,9 @@ import torch.nn as nn
 
 from . import llama as llama_mod
 from . import ops
-from .llama import FlatParams, LlamaCore, LlamaDims, LlamaModelParams, _Linear, init_llama_params_
+from .llama import FlatParams, LlamaCore, LlamaDims, LlamaModelParams, _Linear
 from .parallel import GradSync
-from .tokenizer import SPECIAL_TOKENS, HFTokenizerAdapter, SyntheticTokenizer
+from .tokenizer import HFTokenizerAdapter, SyntheticTokenizer
 
 bf16 = torch.bfloat16
 

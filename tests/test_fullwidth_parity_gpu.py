@@ -242,6 +242,46 @@ def test_navmodel_navigation_fullwidth_vs_oracle(cuda_dev):
         _boundary_check("grad " + k, named[k].grad, ref["grads"][k], truth["grads"][k], k=3.0, floor=5e-2)
 
 
+def test_navmodel_3dqa_lm_loss_fullwidth_vs_oracle(cuda_dev):
+    """The LM-loss path at full width: model('3dqa', training=True) -- panorama encoder over 36 x 1408 views, prompt with 36
+    <cand> tokens + question, answer labels, lm_head on the label rows at the real vocabulary (32006 columns: the odd-width
+    GEMM, the CE kernel over 32006 classes, the [32006, 4096] lm_head wgrad) -- loss and gradients against the oracle."""
+    from oracle import navillm_oracle as O
+    B = 4
+    model, tok = _full_navmodel(cuda_dev, base_vocab=32000)
+    model.train(False)                                   # dropout off; gradients still flow (training=True below)
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    rng = np.random.RandomState(11)
+    g = torch.Generator().manual_seed(11)
+    feats = [torch.randn(36, 1408, generator=g) for _ in range(B)]
+    prompts = ["Scene " + " ".join(["<cand>"] * 36) + " Question " + " ".join(f"w{i}" for i in rng.randint(0, 5000, size=int(rng.randint(200, 330))))
+               + " Answer" for _ in range(B)]
+    answers = [[" ".join(f"w{i}" for i in rng.randint(0, 5000, size=int(rng.randint(4, 17))))] for _ in range(B)]
+    batch = {"question": [""] * B, "prompts": prompts, "answers": answers, "data_type": ["scanqa"] * B}
+    keys = ["lang_model.lm_head.weight", "lang_model.model.norm.weight", "lang_model.model.embed_tokens.weight",
+            "lang_model.model.layers.0.self_attn.q_proj.weight", "lang_model.model.layers.1.mlp.down_proj.weight",
+            "lang_model.model.layers.1.mlp.gate_proj.weight", "img_embeddings.mapper.weight", "img_embeddings.img_linear.weight",
+            "vp_pos_embeddings.0.bias", "token_type_embeddings.weight"]
+
+    def run_oracle(precision):
+        cfg = _oracle_cfg(tok, precision)
+        dt = cfg.lm_dtype
+        sdd = {k: (v.to(dt) if v.dtype == bf16 else v.clone()).requires_grad_(v.is_floating_point()) for k, v in sd.items()}
+        out = O.forward_3dqa(sdd, cfg, dict(batch, features=feats), tok, tok.eos_token, training=True)
+        out["loss"].float().backward()
+        return {"loss": out["loss"].detach().float(), "grads": {k: sdd[k].grad.float() for k in keys}}
+
+    truth, ref = run_oracle("fp32"), run_oracle("amp_bf16")
+    out = model("3dqa", dict(batch, features=[f.to(cuda_dev) for f in feats]), training=True)
+    out.loss.float().backward()
+    torch.cuda.synchronize()
+    _boundary_check("3dqa loss", out.loss.detach(), ref["loss"], truth["loss"])
+    named = dict(model.named_parameters())
+    for k in keys:
+        assert named[k].grad is not None, k
+        _boundary_check("grad " + k, named[k].grad, ref["grads"][k], truth["grads"][k], k=3.0, floor=5e-2)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # (iii) greedy generate at C3's shape: B = 8, 256 <cand> tokens, >= 32 new tokens, vocab 32006
 # ---------------------------------------------------------------------------------------------------------------------

@@ -141,3 +141,45 @@ def test_prefix_reuse_plan_over_a_three_step_rollout():
     cache.max_len = 8
     with pytest.raises(ValueError, match="exceeds the prefix cache length"):
         plan_prefix_reuse(ids, msk, cache, [2, 2], 2, CAND, HIST, CLS)
+
+
+def test_tokenizer_fallback_is_explicit():
+    """A missing / unusable tokenizer directory must not silently turn into hash-derived token ids (pretrained weights would
+    run on garbage): the synthetic stand-in is used only when asked for (from_scratch / model_config.tokenizer)."""
+    import warnings
+
+    import pytest
+    from navillm_b200.modified_lm import ModifiedLlamaForCausalLM
+    cfg = SimpleNamespace(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=1, vocab_size=64, rms_norm_eps=1e-6)
+    lm = ModifiedLlamaForCausalLM(cfg, SimpleNamespace(precision="amp_bf16"))
+    with pytest.raises(RuntimeError, match="tokenizer"):
+        lm.init_tokenizer("/nonexistent/vicuna-7b")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        lm.init_tokenizer("/nonexistent/vicuna-7b", allow_synthetic=True)
+    assert any("SyntheticTokenizer" in str(x.message) for x in w)
+    assert lm.cls_token == ["<cls_1>", "<cls_2>"] and len(lm.special_token_ids) == 5
+
+
+def test_grad_sync_skips_clean_segments_and_tapers_chunks():
+    """GradSync bookkeeping without a process group: the overlap schedule (groups of `chunk` layers, the last group cut into
+    single layers) and the complement of the clean (all-zero) gradient segments."""
+    from navillm_b200.parallel import GradSync
+    gs = GradSync()
+    assert gs.layer_hook(None, [], 8) is None and gs.exchange() == 0          # no process group: nothing armed, nothing sent
+    # the range complement used by exchange(): [lo, hi) minus clean segments
+    def complement(lo, hi, clean):
+        ranges, cur = [], lo
+        for a, b in sorted(clean):
+            a, b = max(a, lo), min(b, hi)
+            if a >= b:
+                continue
+            if a > cur:
+                ranges.append((cur, a))
+            cur = max(cur, b)
+        if cur < hi:
+            ranges.append((cur, hi))
+        return ranges
+    assert complement(100, 1000, [(400, 700)]) == [(100, 400), (700, 1000)]
+    assert complement(100, 1000, [(0, 150), (900, 2000)]) == [(150, 900)]
+    assert complement(100, 1000, []) == [(100, 1000)]
