@@ -200,6 +200,29 @@ int nv_clip_coef(const float* partial, int n_partial, float max_norm, float* sta
 int nv_adamw_flat(void* p, void* g, void* m, void* v, int64_t n, int is_bf16, float lr, float beta1, float beta2, float eps,
                   float weight_decay, int step, const float* clip_state, int write_clipped_grad, void* stream);
 
+/* ---- one decoder layer of the inference forward in ONE call (csrc/layer.cu) ----------------------------------------
+ * transformers LlamaDecoderLayer (reached through models/modified_lm.py:112-116): RMSNorm -> fused qkv projection -> RoPE
+ * -> causal attention over packed rows -> o_proj + residual -> RMSNorm -> gate|up -> SwiGLU -> down + residual, launched
+ * in order on `stream` with every intermediate in the caller's workspace (nv_llama_layer_ws_bytes).  No activations are
+ * kept: this is the forward of evaluation / prefill at small packed batches, where one ctypes call per kernel is the
+ * bottleneck.  kv_mode 0: plain self-attention over the packed rows; 1: also store post-RoPE K/V of the rows in the caches
+ * (prefill of generate); 2: the rows are suffixes of sequences whose prefixes are cached (cached / kv_start / kv_len as in
+ * nv_kv_store_suffix / nv_attn_fwd_kv).  out_rows (nullable, R rows): only these rows are produced (last layer). */
+typedef struct nv_layer_args {
+  const void* x;            /* [T, D] bf16 residual stream in */
+  void* y;                  /* [R or T, D] bf16 residual stream out */
+  const void* ln1; const void* wqkv; const void* wo; const void* ln2; const void* wgu; const void* wd;
+  const int* pos; const void* cos_t; const void* sin_t; const int* cu_seqlens;
+  void* kcache; void* vcache; const int* cached; const int* kv_start; const int* kv_len;
+  const int* out_rows;
+  void* ws; int64_t ws_bytes;
+  int B, T, total_qblocks, Smax, Tkv, kv_mode, R, D, F, H;
+  float eps, scale;
+} nv_layer_args;
+int nv_layer_args_size(void);                           /* sizeof(nv_layer_args): bindings check their mirror against it */
+int64_t nv_llama_layer_ws_bytes(int T, int R, int D, int F);
+int nv_llama_layer_infer(const nv_layer_args* a, void* stream);
+
 /* ---- in-switch gradient all-reduce over NVLS multicast (csrc/nvls_allreduce.cu) ---------------------------------
  * The path's one exchange step (reference: DDP's NCCL all-reduce, tools/optims.py:52-54, fired from the last backward
  * outside no_sync, tasks/agents/mp3d_agent.py:661-667).  Elements [elem_off, elem_off + n) of a symmetric buffer whose

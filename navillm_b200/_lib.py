@@ -41,10 +41,19 @@ def load(build_if_missing: bool = True) -> ctypes.CDLL:
     return _lib
 
 
+class LayerArgs(ctypes.Structure):
+    """nv_layer_args of include/navillm_b200.h (field order and types must match)."""
+    _fields_ = ([(n, ctypes.c_void_p) for n in ("x", "y", "ln1", "wqkv", "wo", "ln2", "wgu", "wd", "pos", "cos_t", "sin_t", "cu_seqlens",
+                                                "kcache", "vcache", "cached", "kv_start", "kv_len", "out_rows", "ws")]
+                + [("ws_bytes", ctypes.c_int64)]
+                + [(n, ctypes.c_int) for n in ("B", "T", "total_qblocks", "Smax", "Tkv", "kv_mode", "R", "D", "F", "H")]
+                + [("eps", ctypes.c_float), ("scale", ctypes.c_float)])
+
+
 launch_count = 0          # kernels launched through the C ABI since import (bench.py reports the per-step delta)
 
 # entry points that launch more than one kernel per call
-_MULTI = {"nv_rmsnorm_bwd": 2, "nv_attn_bwd": 3, "nv_layernorm_bwd": 3, "nv_head_bwd": 2, "nv_mha_bwd": 2}
+_MULTI = {"nv_rmsnorm_bwd": 2, "nv_attn_bwd": 3, "nv_layernorm_bwd": 3, "nv_head_bwd": 2, "nv_mha_bwd": 2, "nv_llama_layer_infer": 10}
 
 
 def check(status: int, what: str) -> None:

@@ -278,8 +278,31 @@ class LlamaCore:
             self.gd[l] = m.down_proj.weight.grad
 
     # -------------------------------------------------------------------------------------------------
+    # packed batches below this many rows run the inference forward through ONE C-ABI call per layer (csrc/layer.cu):
+    # they are host-bound when every kernel is its own call from Python
+    LAYER_CALL = os.environ.get("NAVILLM_LAYER_CALL", "1") != "0"
+
+    def _forward_layer_calls(self, x, pos, cu, seqlens, kv_store, out_rows):
+        d = self.d
+        T = x.shape[0]
+        R = 0 if out_rows is None else out_rows.numel()
+        run = ops.LayerRunner(T, d.hidden, d.inter, d.n_heads, d.rms_eps, pos, self.cos, self.sin, cu, len(seqlens), ops._qblocks(seqlens),
+                              R=R, device=x.device)
+        if kv_store is not None:
+            run.set_cache_mode(1, kv_store[0][0].shape[1])
+        bufs = [torch.empty_like(x), torch.empty_like(x)]
+        last = d.n_layers - 1
+        for l, lyr in enumerate(self.model.layers):
+            pruned = out_rows is not None and l == last
+            y = torch.empty((R, d.hidden), dtype=bf16, device=x.device) if pruned else bufs[l & 1]
+            run.run(x, y, lyr.input_layernorm.weight.data, self.wqkv[l], self.wo[l], lyr.post_attention_layernorm.weight.data, self.wgu[l],
+                    self.wd[l], kc=kv_store[0][l] if kv_store is not None else None, vc=kv_store[1][l] if kv_store is not None else None,
+                    out_rows=out_rows if pruned else None)
+            x = y
+        return x
+
     def forward(self, x: torch.Tensor, pos: torch.Tensor, cu: torch.Tensor, seqlens, save: bool = True, kv_sink=None,
-                out_rows: Optional[torch.Tensor] = None):
+                out_rows: Optional[torch.Tensor] = None, kv_store=None):
         """x: [T, D] bf16 input embeddings (packed); pos: int32 [T]; cu: int32 [B+1] (device); seqlens: host
         lengths.  Returns (residual stream after the last layer BEFORE the final RMSNorm, tape) where ``tape``
         holds the per-layer activations for ``backward`` (None when save=False).  The tape travels with the
@@ -295,6 +318,11 @@ class LlamaCore:
         last = d.n_layers - 1
         # fused-epilogue kernels (CTA-pair GEMM) need head_dim 128, F % 128 == 0 and at least one wave of tiles
         fused = self.fused_epilogues and x.shape[0] >= 1024 and d.inter % 128 == 0 and d.hidden % 256 == 0
+        if kv_store is not None and kv_sink is None:                  # (kc list, vc list): post-RoPE K, V of every layer go to the caches
+            B_, T_ = len(seqlens), x.shape[0]
+            kv_sink = lambda l, qkv: ops.kv_store_prefill(qkv, cu, kv_store[0][l], kv_store[1][l], B_, T_)
+        if self.LAYER_CALL and not save and not fused and d.head_dim == 128 and (kv_store is not None or kv_sink is None):
+            return self._forward_layer_calls(x, pos, cu, seqlens, kv_store, out_rows), None
         for l, lyr in enumerate(self.model.layers):
             s = _Saved()
             s.x = x
@@ -340,6 +368,18 @@ class LlamaCore:
         B, T = len(q_lens), x.shape[0]
         last = d.n_layers - 1
         fused = self.fused_epilogues and T >= 1024 and d.inter % 128 == 0 and d.hidden % 256 == 0
+        if self.LAYER_CALL and not fused and d.head_dim == 128:
+            R = 0 if out_rows is None else out_rows.numel()
+            run = ops.LayerRunner(T, D, d.inter, H, d.rms_eps, pos, self.cos, self.sin, cu, B, ops._qblocks(q_lens), R=R, device=x.device)
+            run.set_cache_mode(2, kc[0].shape[1], kc[0].shape[0] * kc[0].shape[1], cached, kv_start, kv_len)
+            bufs = [torch.empty_like(x), torch.empty_like(x)]
+            for l, lyr in enumerate(self.model.layers):
+                pruned = out_rows is not None and l == last
+                y = torch.empty((R, D), dtype=bf16, device=x.device) if pruned else bufs[l & 1]
+                run.run(x, y, lyr.input_layernorm.weight.data, self.wqkv[l], self.wo[l], lyr.post_attention_layernorm.weight.data,
+                        self.wgu[l], self.wd[l], kc=kc[l], vc=vc[l], out_rows=out_rows if pruned else None)
+                x = y
+            return x
         for l, lyr in enumerate(self.model.layers):
             xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
             if fused:

@@ -538,12 +538,9 @@ class ModifiedLlamaForCausalLM(nn.Module):
         finished.zero_()
         lens.copy_(torch.tensor(pp.seqlens, dtype=torch.int32), non_blocking=True)
 
-        def sink(l, qkv):
-            ops.kv_store_prefill(qkv, pp.cu, kc[l], vc[l], B, pp.T)
-
         E = self.model.embed_tokens.weight.data
         x = ops.embed_fwd(pp.ids, E, pp.vis_src if vis is not None else None, vis)
-        hid_last, _ = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=False, kv_sink=sink, out_rows=pp.last_rows)
+        hid_last, _ = core.forward(x, pp.pos, pp.cu, pp.seqlens, save=False, kv_store=(kc, vc), out_rows=pp.last_rows)
         special = self.special_ids_dev
 
         def head(h_rows):

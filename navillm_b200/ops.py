@@ -539,6 +539,48 @@ def argmax_masked(logits, special, finished, eos_id, pad_id, stop_on_eos, next_i
     return next_ids
 
 
+class LayerRunner:
+    """Inference forward of decoder layers through nv_llama_layer_infer (csrc/layer.cu): ONE C-ABI call per layer instead of
+    ten.  Holds the argument block and a workspace for a given packing; ``run`` fills in what changes per layer."""
+
+    def __init__(self, T: int, D: int, F: int, H: int, eps: float, pos, cos_t, sin_t, cu, B: int, total_qblocks: int, *, R: int = 0,
+                 device=None, scale: float | None = None):
+        lib = _lib.load()
+        lib.nv_llama_layer_ws_bytes.restype = ctypes.c_int64
+        self.T, self.D, self.R = T, D, R
+        nbytes = max(int(lib.nv_llama_layer_ws_bytes(i32(T), i32(R), i32(D), i32(F))), int(lib.nv_llama_layer_ws_bytes(i32(T), i32(0), i32(D), i32(F))))
+        self.ws = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        a = _lib.LayerArgs()
+        a.pos, a.cos_t, a.sin_t, a.cu_seqlens = pos.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), cu.data_ptr()
+        a.ws, a.ws_bytes = self.ws.data_ptr(), nbytes
+        a.B, a.T, a.total_qblocks, a.D, a.F, a.H = B, T, total_qblocks, D, F, H
+        a.eps, a.scale = eps, (128 ** -0.5 if scale is None else scale)
+        a.kv_mode = 0
+        self.args = a
+        self._keep = (pos, cos_t, sin_t, cu)
+
+    def set_cache_mode(self, mode: int, Smax: int, Tkv: int = 0, cached=None, kv_start=None, kv_len=None):
+        a = self.args
+        a.kv_mode, a.Smax, a.Tkv = mode, Smax, Tkv
+        a.cached = cached.data_ptr() if cached is not None else None
+        a.kv_start = kv_start.data_ptr() if kv_start is not None else None
+        a.kv_len = kv_len.data_ptr() if kv_len is not None else None
+        self._keep += (cached, kv_start, kv_len)
+
+    def run(self, x, y, ln1, wqkv, wo, ln2, wgu, wd, *, kc=None, vc=None, out_rows=None):
+        a = self.args
+        a.x, a.y = x.data_ptr(), y.data_ptr()
+        a.ln1, a.wqkv, a.wo, a.ln2, a.wgu, a.wd = ln1.data_ptr(), wqkv.data_ptr(), wo.data_ptr(), ln2.data_ptr(), wgu.data_ptr(), wd.data_ptr()
+        a.kcache = kc.data_ptr() if kc is not None else None
+        a.vcache = vc.data_ptr() if vc is not None else None
+        if out_rows is not None:
+            a.out_rows, a.R = out_rows.data_ptr(), out_rows.numel()
+        else:
+            a.out_rows, a.R = None, 0
+        check(_lib.load().nv_llama_layer_infer(ctypes.byref(a), stream_ptr()), "nv_llama_layer_infer")
+        return y
+
+
 class pdl:
     """Context: launch the decode-chain kernels with programmatic dependent launch (nv_set_pdl)."""
 

@@ -69,3 +69,10 @@ def test_sass_contains_blackwell_tensor_and_tma_instructions():
                          capture_output=True, text=True).stdout
     assert "UTCHMMA" in out and "UTMALDG" in out and "LDTM" in out
     assert "HMMA." not in out.replace("UTCHMMA", ""), "legacy mma.sync path found"
+
+
+def test_layer_args_mirror_matches_the_c_struct():
+    """ctypes mirror of nv_layer_args (navillm_b200/_lib.py) against sizeof in the library."""
+    import ctypes
+    from navillm_b200 import _lib
+    assert _lib.load(build_if_missing=False).nv_layer_args_size() == ctypes.sizeof(_lib.LayerArgs)

@@ -92,3 +92,38 @@ def test_llama_stack_forward_backward(cuda_dev):
               "layers.0.mlp.gate_proj.weight", "layers.1.mlp.up_proj.weight", "layers.1.mlp.down_proj.weight",
               "layers.0.input_layernorm.weight", "layers.1.post_attention_layernorm.weight", "norm.weight"):
         check(k, named[k].grad.float().cpu(), gw_truth["lang_model.model." + k], gw_ref["lang_model.model." + k])
+
+
+def test_layer_call_inference_forward_is_bit_identical(cuda_dev):
+    """The one-call-per-layer inference forward (nv_llama_layer_infer, csrc/layer.cu) launches the same kernels as the
+    per-kernel path: residual stream bit-identical, with and without last-layer row pruning and with the K/V store of a
+    generate() prefill."""
+    cfg, sd, dims, model, flat, core = build(cuda_dev)
+    B, S, D = 3, 200, dims.hidden
+    lens = [37, 200, 130]
+    g = torch.Generator().manual_seed(12)
+    emb = (torch.randn(B, S, D, generator=g) * 0.5).to(bf16)
+    mask = torch.zeros(B, S, dtype=torch.long)
+    for b, L in enumerate(lens):
+        mask[b, S - L:] = 1
+    rows, pos, cu, seqlens = pack(emb, mask)
+    x = emb.view(B * S, D)[rows].to(cuda_dev).contiguous()
+    pos, cu = pos.to(cuda_dev), cu.to(cuda_dev)
+    out_rows = torch.tensor([36, 236, 366], dtype=torch.int32, device=cuda_dev)          # last row of every sequence
+    Smax = 256
+    results = {}
+    for mode in (True, False):
+        core.LAYER_CALL = mode
+        kc = [torch.zeros((B, Smax, D), dtype=bf16, device=cuda_dev) for _ in range(dims.n_layers)]
+        vc = [torch.zeros((B, Smax, D), dtype=bf16, device=cuda_dev) for _ in range(dims.n_layers)]
+        full, tape = core.forward(x, pos, cu, seqlens, save=False)
+        pruned, _ = core.forward(x, pos, cu, seqlens, save=False, out_rows=out_rows, kv_store=(kc, vc))
+        torch.cuda.synchronize()
+        assert tape is None
+        results[mode] = (full.clone(), pruned.clone(), [k.clone() for k in kc], [v.clone() for v in vc])
+    core.LAYER_CALL = type(core).LAYER_CALL
+    a, b = results[True], results[False]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert torch.equal(a[1], a[0][out_rows.long()])                    # pruning = row selection of the full forward
+    for l in range(dims.n_layers):
+        assert torch.equal(a[2][l], b[2][l]) and torch.equal(a[3][l], b[3][l])
