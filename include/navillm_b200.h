@@ -189,6 +189,12 @@ int nv_decode_attn_rope(const void* qkv, int64_t ld, const int* lens, const void
 int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id,
                      int pad_id, int stop_on_eos, int* next, int B, void* stream);
 int nv_add_int(int* x, int n, int delta, void* stream);
+/* Sampled next token = HF GenerationMixin.sample as reached with do_sample=True (tasks/agents/llava.py:58-62 ->
+ * models/nav_model.py:388-396): scores / temperature (bf16) -> top-k (transformers' generation default 50; ties at the k-th
+ * value stay; top_k <= 0: off) -> softmax (bf16 output) -> inverse-CDF draw at u[b] in [0,1).  Special tokens masked,
+ * finished / eos / pad handling as nv_argmax_masked.  probs_out: optional fp32 [B, V] copy of the distribution drawn from. */
+int nv_sample_topk(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id, int pad_id,
+                   int stop_on_eos, float temperature, int top_k, const float* u, int* next, float* probs_out, int B, void* stream);
 
 /* ---- fused clip + AdamW over flat buffers (csrc/optim.cu) ------------------------------------------------------
  * torch.nn.utils.clip_grad_norm_(model.parameters(), 40.) + torch.optim.AdamW.step() of the reference

@@ -340,6 +340,157 @@ __global__ void add_int_kernel(int* __restrict__ x, int n, int delta) {
   if (i < n) x[i] += delta;
 }
 
+// ---- sampled decoding (HF GenerationMixin.sample as the reference reaches it with do_sample=True, tasks/agents/llava.py:58-62
+// -> models/nav_model.py:388-396): next-token scores -> TemperatureLogitsWarper (scores / T, in the logits' dtype: bf16) ->
+// TopKLogitsWarper (transformers' generation default top_k = 50: every score strictly below the k-th largest becomes -inf,
+// ties at the k-th value stay) -> softmax (fp32 inside, rounded to bf16) -> one multinomial draw.  One CTA per row: the
+// row's scores live in shared memory, the k-th largest is found exactly with two 8-bit radix passes over the 16 significant
+// bits of a bf16 value, and the draw is the inverse CDF (token order) of the bf16 probabilities at the uniform number u[b]
+// the host supplies (torch.rand: the torch CUDA generator stays the seed authority, like torch.multinomial in the reference).
+// finished / eos / pad handling as argmax_kernel.  probs_out (optional, fp32 [B, V]) receives the sampling distribution.
+constexpr int SMP_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t smp_key16(float v) {          // monotone: larger float -> larger key; -inf lowest
+  uint32_t u = __float_as_uint(v);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return u >> 16;
+}
+
+// threads cooperatively find, scanning bins from the top, the bin that holds the `want`-th largest element (1-based);
+// returns that bin and how many elements sit in higher bins.  hist: 256 counters in shared memory.
+__device__ __forceinline__ void smp_pick_bin(const int* hist, int want, int& bin, int& above) {
+  __shared__ int s_bin, s_above;
+  if (threadIdx.x == 0) {
+    int acc = 0, b = 255;
+    for (; b > 0; --b) {
+      if (acc + hist[b] >= want) break;
+      acc += hist[b];
+    }
+    s_bin = b;
+    s_above = acc;
+  }
+  __syncthreads();
+  bin = s_bin;
+  above = s_above;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SMP_THREADS) sample_topk_kernel(const __nv_bfloat16* __restrict__ logits, int64_t ld, int V,
+                                                                  const int* __restrict__ special, int n_special,
+                                                                  int* __restrict__ finished, int eos_id, int pad_id, int stop_on_eos,
+                                                                  float temperature, int top_k, const float* __restrict__ u,
+                                                                  int* __restrict__ next, float* __restrict__ probs_out) {
+  extern __shared__ float sc[];                              // [V] scores, then probabilities
+  __shared__ int hist[256];
+  __shared__ float red[32];
+  __shared__ int s_special[64];
+  __shared__ int s_idx, s_last;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int ns = min(n_special, 64);
+  if (tid < ns) s_special[tid] = special[tid];
+  if (tid < 256) hist[tid] = 0;
+  if (tid == 0) { s_idx = V; s_last = -1; }
+  __syncthreads();
+  const __nv_bfloat16* row = logits + (int64_t)b * ld;
+  // 1. scores = bf16(logit / T), special tokens -inf (models/modified_lm.py:122-124); histogram of the high key byte
+  float mx = -INFINITY;
+  for (int c = tid; c < V; c += SMP_THREADS) {
+    bool sp = false;
+    for (int s = 0; s < ns; ++s) sp |= (s_special[s] == c);
+    float v = sp ? -INFINITY : bf16_round(__bfloat162float(row[c]) / temperature);
+    if (v != v) v = -INFINITY;                               // NaN scores cannot be drawn
+    sc[c] = v;
+    mx = fmaxf(mx, v);
+    atomicAdd(&hist[smp_key16(v) >> 8], 1);
+  }
+  __syncthreads();
+  // 2. the k-th largest score, exactly
+  const int k = max(1, min(top_k > 0 ? top_k : V, V));
+  int hi_bin, above;
+  smp_pick_bin(hist, k, hi_bin, above);
+  if (tid < 256) hist[tid] = 0;
+  __syncthreads();
+  for (int c = tid; c < V; c += SMP_THREADS) {
+    const uint32_t key = smp_key16(sc[c]);
+    if ((int)(key >> 8) == hi_bin) atomicAdd(&hist[key & 255u], 1);
+  }
+  __syncthreads();
+  int lo_bin, above2;
+  smp_pick_bin(hist, k - above, lo_bin, above2);
+  const uint32_t thr_key = ((uint32_t)hi_bin << 8) | (uint32_t)lo_bin;      // keep score >= k-th largest (ties stay)
+  // 3. softmax over the kept scores (fp32), rounded to bf16 like the reference's bf16 softmax output
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[w] = mx;
+  __syncthreads();
+  mx = red[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  __syncthreads();
+  float part = 0.f;
+  for (int c = tid; c < V; c += SMP_THREADS) {
+    const float v = sc[c];
+    const float e = (smp_key16(v) >= thr_key && v > -INFINITY) ? expf(v - mx) : 0.f;
+    sc[c] = e;
+    part += e;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+  if (lane == 0) red[w] = part;
+  __syncthreads();
+  float denom = red[lane];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) denom += __shfl_xor_sync(0xffffffffu, denom, o);
+  __syncthreads();
+  // 4. probabilities + inverse CDF in token order: thread t owns the contiguous chunk [t*CH, (t+1)*CH)
+  const int CH = (V + SMP_THREADS - 1) / SMP_THREADS;
+  const int c0 = min(tid * CH, V), c1 = min(c0 + CH, V);
+  float local = 0.f;
+  int last_kept = -1;
+  for (int c = c0; c < c1; ++c) {
+    const float p = bf16_round(sc[c] / denom);
+    sc[c] = p;
+    local += p;
+    if (p > 0.f) last_kept = c;
+    if (probs_out) probs_out[(int64_t)b * V + c] = p;
+  }
+  if (last_kept >= 0) atomicMax(&s_last, last_kept);
+  float incl = local;                                        // inclusive scan of the chunk sums over the CTA
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) red[w] = incl;
+  __syncthreads();
+  float wsum = red[lane];
+  float wincl = wsum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const float t = __shfl_up_sync(0xffffffffu, wincl, o);
+    if (lane >= o) wincl += t;
+  }
+  const float total = __shfl_sync(0xffffffffu, wincl, 31);
+  const float wprefix = __shfl_sync(0xffffffffu, wincl - wsum, w);   // sum of the warps before this one
+  const float prefix = wprefix + incl - local;
+  const float target = u[b] * total;
+  if (prefix + local > target) {
+    float run = prefix;
+    for (int c = c0; c < c1; ++c) {
+      run += sc[c];
+      if (run > target && sc[c] > 0.f) { atomicMin(&s_idx, c); break; }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int tok = s_idx < V ? s_idx : s_last;                    // rounding pushed the target to the total: last kept token
+    if (tok < 0) tok = pad_id;                               // every score -inf (cannot happen with a live row)
+    if (finished[b]) tok = pad_id;
+    else if (stop_on_eos && tok == eos_id) finished[b] = 1;
+    next[b] = tok;
+  }
+}
+
 }  // namespace nv
 
 using namespace nv;
@@ -421,6 +572,24 @@ int nv_argmax_masked(const void* logits, int64_t ld, int V, const int* special, 
   if (B == 0) return NV_OK;
   NV_CUDA(launch_pdl(argmax_kernel, dim3(B), dim3(1024), 0, S_(stream), CBF(logits), ld, V, special, n_special, finished, eos_id, pad_id,
                      stop_on_eos, next));
+  return NV_OK;
+}
+
+// Sampled next token (HF sample: temperature -> top-k -> softmax -> multinomial); see sample_topk_kernel.  logits [B, V] bf16,
+// u [B] uniform numbers in [0, 1), probs_out: optional fp32 [B, V] copy of the sampling distribution (tests).
+int nv_sample_topk(const void* logits, int64_t ld, int V, const int* special, int n_special, int* finished, int eos_id, int pad_id,
+                   int stop_on_eos, float temperature, int top_k, const float* u, int* next, float* probs_out, int B, void* stream) {
+  NV_REQUIRE(logits && u && next && finished && V > 0 && temperature > 0.f, "nv_sample_topk: bad arguments (temperature must be > 0)");
+  NV_REQUIRE((int64_t)V * 4 <= 200 * 1024, "nv_sample_topk: vocabulary of %d does not fit the shared-memory score row", V);
+  if (B == 0) return NV_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NV_CUDA(cudaFuncSetAttribute(sample_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  sample_topk_kernel<<<B, SMP_THREADS, (size_t)V * 4, S_(stream)>>>(CBF(logits), ld, V, special, n_special, finished, eos_id, pad_id,
+                                                                     stop_on_eos, temperature, top_k, u, next, probs_out);
+  NV_LAUNCH_CHECK();
   return NV_OK;
 }
 

@@ -291,6 +291,15 @@ extern "C" int nv_gemm_bf16(const void* A, int64_t lda, int a_mn, const void* B,
   if (block_n == 0) {
     const long pair_tiles = ((long)(M + 255) / 256) * ((long)(N + 255) / 256);
     block_n = (pair_tiles >= sm_count() / 2 && M >= 512) ? 512 : (M <= 128) ? 128 : (N >= 2048 ? 256 : 128);
+    // 16 < M < 512 (one forward of a small batch, evaluation rollouts, prefix-reuse suffixes): weight streaming, and the
+    // tile shape decides how many SMs pull on HBM.  Measured per variant at M = 48..384 on the four Vicuna-7B
+    // projections (tools/midm_bench.py, profiles/r02_midm_gemm.txt); every variant accumulates the k-blocks in the same
+    // order, so the choice does not change a single output bit.
+    if (M < 512 && !a_mn && !b_mn) {
+      if (M <= 128) block_n = N <= 4096 ? 32 : (N >= 16384 ? 256 : 128);
+      else if (M <= 256) block_n = (N <= 4096 || N >= 16384) ? 128 : 512;
+      else block_n = N <= 4096 ? 128 : 256;
+    }
   }
   if (block_n == 512)   // CTA-pair kernel (cta_group::2), 256 x 256 tile per SM pair
     return gemm_bf16_2cta_dispatch(A, lda, a_mn, B, ldb, b_mn, C, ldc, addend, ld_add, M, N, K, flags, stream);

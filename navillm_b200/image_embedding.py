@@ -15,7 +15,10 @@ counter-based RNG keyed by (torch.cuda.initial_seed(), call counter, site): the 
 stream (which the reference consumes in ``forward_navigation``) is untouched, and a run is reproducible after
 ``torch.manual_seed``.  The random STREAM differs from torch's Philox, so train-mode outputs match the reference in
 distribution, not element-wise; element-wise parity is defined in ``eval()``.
-``fuse_obj`` (off in every reference config) is unsupported.
+``fuse_obj`` (``--fuse_obj``, tools/parser.py:95; off in the released configs) is the reference's branch
+models/image_embedding.py:78-94: object tokens join the views in the encoder input; built on the same kernels through
+row-index maps (``_fuse_maps``), forward and backward, and checked against the reference's own module
+(tests/golden/pano_fuse_obj.pt).
 """
 from __future__ import annotations
 
@@ -86,7 +89,7 @@ class _PanoFn(torch.autograd.Function):
     reaches ``backward`` below, which accumulates every parameter gradient natively."""
 
     @staticmethod
-    def forward(ctx, mod: "ImageEmbeddings", view, lens32, loc, types32, keep_idx, anchor):
+    def forward(ctx, mod: "ImageEmbeddings", view, lens32, loc, types32, keep_idx, anchor, fuse=None):
         B, N, Dv = view.shape
         R = B * N
         v2 = view.reshape(R, Dv)
@@ -110,7 +113,25 @@ class _PanoFn(torch.autograd.Function):
             x = ops.dropout(x, p_emb, seed)
         layers = []
         enc = mod.pano_encoder
+        Ne, lens_e = N, lens32                         # the encoder's view of the batch (fuse_obj: views + objects per row)
+        if enc is not None and fuse is not None:
+            # `--fuse_obj` (models/image_embedding.py:78-94): object tokens = obj_linear (Linear + LN) + the SHARED
+            # LN(loc_linear(obj_loc_fts)) + nav-type 2 - not through layer_norm / dropout - appended to each row's views
+            obj, obj_loc = fuse["obj"], fuse["obj_loc"]
+            O_ = obj.shape[1]
+            t["o2"] = obj.reshape(B * O_, obj.shape[-1])
+            t["ox"] = _lin_fwd(t["o2"], mod.obj_linear[0])
+            oa, t["m_o"], t["r_o"] = _ln_fwd(t["ox"], mod.obj_linear[1])
+            t["oloc2"] = obj_loc.reshape(B * O_, obj_loc.shape[-1])
+            t["oxloc"] = _lin_fwd(t["oloc2"], mod.loc_linear)
+            oe, t["m_oloc"], t["r_oloc"] = _ln_fwd(t["oxloc"], mod.loc_layer_norm, addend=oa)
+            ops.rows_combine(oe, b=mod.nav_type_embedding.weight.data, ib=fuse["twos"], accumulate=True)
+            Ne, lens_e = fuse["Nf"], fuse["lens_f"]
+            xf = torch.empty((B * Ne, x.shape[1]), dtype=f32, device=x.device)
+            ops.rows_combine(xf, a=x, ia=fuse["view_src"], b=oe, ib=fuse["obj_src"])       # pad rows: zeros (pad_tensors_wgrad)
+            x = xf
         if enc is not None:
+            N, lens32, R = Ne, lens_e, B * Ne
             for li, lyr in enumerate(enc.layers):
                 s = {"x": x}
                 sd = seed + 16 * (li + 1)
@@ -138,6 +159,11 @@ class _PanoFn(torch.autograd.Function):
                     _lin_fwd(s["a1"], lyr.linear2, out=x2, accumulate=True)
                     x = x2
                 layers.append(s)
+            if fuse is not None:                       # the view rows come back (:92-93); the final LayerNorm is row-wise
+                N, R = view.shape[1], B * view.shape[1]
+                xv = torch.empty((R, x.shape[1]), dtype=f32, device=x.device)
+                ops.rows_combine(xv, a=x, ia=fuse["view_back"])
+                x = xv
             t["xe"] = x
             x, t["m_f"], t["r_f"] = _ln_fwd(x, enc.norm)
         t["y"] = x
@@ -146,7 +172,9 @@ class _PanoFn(torch.autograd.Function):
         ops.rows_combine(out, a=m, ia=keep_idx)       # zero the padded rows (image_embedding.py:103)
         ctx.mod, ctx.t, ctx.layers = mod, t, layers
         ctx.dims = (B, N)
-        ctx.lens32, ctx.types32, ctx.keep_idx = lens32, types32, keep_idx
+        ctx.enc_dims = (Ne, lens_e)
+        ctx.fuse = fuse
+        ctx.types32, ctx.keep_idx = types32, keep_idx
         return out.view(B, N, -1)
 
     @staticmethod
@@ -159,8 +187,16 @@ class _PanoFn(torch.autograd.Function):
         ops.rows_combine(dm, a=dout, ia=ctx.keep_idx)               # padded rows carry no gradient
         dx = _lin_bwd(dm, t["y"], mod.mapper)
         enc = mod.pano_encoder
+        fuse = ctx.fuse
         if enc is not None:
             dx = _ln_bwd(dx, t["xe"], enc.norm, t["m_f"], t["r_f"])
+            if fuse is not None:                       # gradient of the view rows into the fused layout; object / pad rows: 0
+                N, lens_e = ctx.enc_dims
+                R = B * N
+                dxf = torch.empty((R, dx.shape[1]), dtype=f32, device=dx.device)
+                ops.rows_combine(dxf, a=dx, ia=fuse["view_src"])
+                dx = dxf
+            lens32 = ctx.enc_dims[1]
             p_l, seed = t["p_l"], t["seed"]
             n_l = len(layers)
             for li, (lyr, s) in enumerate(zip(reversed(list(enc.layers)), reversed(layers))):
@@ -176,16 +212,31 @@ class _PanoFn(torch.autograd.Function):
                 dy1 = ops.dropout(dx1, p_l, sd + 1) if p_l > 0 else dx1               # dropout1
                 datt = _lin_bwd(dy1, s["att"], lyr.self_attn.out_proj)
                 if p_l > 0:
-                    dqkv = ops.mha_bwd_dropout(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], s["Pd"], ctx.lens32,
+                    dqkv = ops.mha_bwd_dropout(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], s["Pd"], lens32,
                                                mod.num_heads).view(R, -1)
                 else:
-                    dqkv = ops.mha_bwd(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], ctx.lens32, mod.num_heads).view(R, -1)
+                    dqkv = ops.mha_bwd(s["qkv"].view(B, N, -1), datt.view(B, N, -1), s["P"], lens32, mod.num_heads).view(R, -1)
                 sa = lyr.self_attn
                 ops.sgemm(dqkv, s["h"], ta=True, tb=True, out=_grad(sa.in_proj_weight), accumulate=True)
                 ops.colsum_(dqkv, _grad(sa.in_proj_bias), accumulate=True)
                 dh = ops.sgemm(dqkv, sa.in_proj_weight.data, tb=True)
                 dx = dx1
                 _ln_bwd(dh, s["x"], lyr.norm1, s["m1"], s["r1"], dx=dx, accumulate_dx=True)
+        if enc is not None and fuse is not None:
+            # split the fused gradient: object rows -> obj_linear / shared loc branch / nav-type row 2; view rows go on
+            O_ = t["o2"].shape[0] // B
+            d_oe = torch.empty((B * O_, dx.shape[1]), dtype=f32, device=dx.device)
+            ops.rows_combine(d_oe, a=dx, ia=fuse["obj_back"])
+            ops.rows_scatter_add_(_grad(mod.nav_type_embedding.weight), fuse["twos"], d_oe)
+            d_oxloc = _ln_bwd(d_oe, t["oxloc"], mod.loc_layer_norm, t["m_oloc"], t["r_oloc"])
+            _lin_bwd(d_oxloc, t["oloc2"], mod.loc_linear, need_dx=False)
+            d_ox = _ln_bwd(d_oe, t["ox"], mod.obj_linear[1], t["m_o"], t["r_o"])
+            _lin_bwd(d_ox, t["o2"], mod.obj_linear[0], need_dx=False)
+            N = ctx.dims[1]
+            R = B * N
+            dxv = torch.empty((R, dx.shape[1]), dtype=f32, device=dx.device)
+            ops.rows_combine(dxv, a=dx, ia=fuse["view_back"])
+            dx = dxv
         if t["p_emb"] > 0:
             dx = ops.dropout(dx.contiguous(), t["p_emb"], t["seed"])
         dc = _ln_bwd(dx, t["c"], mod.layer_norm, t["m_ln"], t["r_ln"])
@@ -195,7 +246,7 @@ class _PanoFn(torch.autograd.Function):
         dximg = _ln_bwd(dc, t["ximg"], mod.img_layer_norm, t["m_img"], t["r_img"])
         _lin_bwd(dximg, t["v2"], mod.img_linear, need_dx=False)
         ctx.t = ctx.layers = None
-        return None, None, None, None, None, None, None
+        return None, None, None, None, None, None, None, None
 
 
 class _ObjFn(torch.autograd.Function):
@@ -228,8 +279,6 @@ def gen_seq_masks(seq_lens: torch.Tensor, max_len=None) -> torch.Tensor:
 class ImageEmbeddings(nn.Module):
     def __init__(self, config, use_obj: bool = False, fuse_obj: bool = False):
         super().__init__()
-        if fuse_obj:
-            raise NotImplementedError("fuse_obj=True is off in every reference config and not built (round 1)")
         H = config.hidden_size
         self.num_heads = config.num_attention_heads
         self.img_linear = nn.Linear(config.image_feat_size, H)
@@ -238,10 +287,13 @@ class ImageEmbeddings(nn.Module):
         self.loc_layer_norm = nn.LayerNorm(H, eps=1e-12)
         self.fuse_obj = fuse_obj
         if use_obj:
+            if fuse_obj:                                # registered before obj_projector, like the reference (:21-30)
+                self.obj_linear = nn.Sequential(nn.Linear(config.obj_feat_size, H), nn.LayerNorm(H, eps=1e-12))
             self.obj_projector = nn.Sequential(nn.Linear(config.obj_feat_size, config.output_size),
                                                nn.LayerNorm(config.output_size, eps=1e-12))
         else:
             self.obj_projector = None
+            self.obj_linear = None
         self.nav_type_embedding = nn.Embedding(3, H)
         self.layer_norm = nn.LayerNorm(H, eps=1e-12)
         self.dropout = nn.Dropout(config.hidden_dropout_prob)
@@ -254,6 +306,35 @@ class ImageEmbeddings(nn.Module):
         # autograd anchor: a 0-d tensor that requires grad so the Function's outputs get a grad_fn even
         # though no *input tensor* of the encoder needs a gradient (parameters are updated natively)
         self.register_buffer("_anchor", torch.zeros((), dtype=f32), persistent=False)
+
+    def _fuse_maps(self, view_lens, obj_img_fts, obj_lens, obj_loc_fts, B, N, dev):
+        """Index maps of the `fuse_obj` layout (models/image_embedding.py:81-93): row b of the encoder input is
+        [views[b, :view_lens[b]] ; objs[b, :obj_lens[b]]] zero-padded to max_b(view_lens + obj_lens).  The lengths are
+        host values in the agent (the reference reads them on the host too: `:view_lens[bn]` slices, gen_seq_masks max)."""
+        if getattr(self, "obj_linear", None) is None:
+            raise RuntimeError("fuse_obj=True needs a model built with enable_og=True (obj_linear is only created then, "
+                               "models/image_embedding.py:21-26)")
+        if obj_img_fts is None or obj_lens is None or obj_loc_fts is None:
+            raise ValueError("fuse_obj=True: obj_img_fts, obj_lens and obj_loc_fts are required (models/image_embedding.py:79-80)")
+        vl = [int(v) for v in view_lens.tolist()]
+        ol = [int(v) for v in obj_lens.tolist()]
+        O_ = obj_img_fts.shape[1]
+        Nf = max(v + w for v, w in zip(vl, ol))
+        view_src, obj_src = [-1] * (B * Nf), [-1] * (B * Nf)
+        view_back, obj_back = [-1] * (B * N), [-1] * (B * O_)
+        for b in range(B):
+            for j in range(vl[b]):
+                view_src[b * Nf + j] = b * N + j
+                view_back[b * N + j] = b * Nf + j
+            for j in range(ol[b]):
+                obj_src[b * Nf + vl[b] + j] = b * O_ + j
+                obj_back[b * O_ + j] = b * Nf + vl[b] + j
+        maps = torch.tensor(view_src + obj_src + view_back + obj_back + [v + w for v, w in zip(vl, ol)] + [2] * (B * O_),
+                            dtype=torch.int32).to(dev, non_blocking=True)                    # one upload
+        o = [0, B * Nf, 2 * B * Nf, 2 * B * Nf + B * N, 2 * B * Nf + B * N + B * O_, 2 * B * Nf + B * N + B * O_ + B]
+        return {"Nf": Nf, "view_src": maps[o[0]:o[1]], "obj_src": maps[o[1]:o[2]], "view_back": maps[o[2]:o[3]],
+                "obj_back": maps[o[3]:o[4]], "lens_f": maps[o[4]:o[5]].contiguous(), "twos": maps[o[5]:],
+                "obj": obj_img_fts.to(f32).contiguous(), "obj_loc": obj_loc_fts.to(f32).contiguous()}
 
     def forward_panorama_per_step(self, view_img_fts, view_lens, loc_fts=None, nav_types=None, obj_img_fts=None,
                                   obj_lens=None, obj_loc_fts=None):
@@ -272,8 +353,11 @@ class ImageEmbeddings(nn.Module):
         rows = torch.arange(B * N, device=dev, dtype=torch.int32)
         keep_idx = torch.where(pano_masks.reshape(-1), rows, torch.full_like(rows, -1))
         anchor = self._anchor.detach().requires_grad_(torch.is_grad_enabled())
+        fuse = None
+        if self.fuse_obj and self.pano_encoder is not None:
+            fuse = self._fuse_maps(view_lens, obj_img_fts, obj_lens, obj_loc_fts, B, N, dev)
         pano = _PanoFn.apply(self, view, lens32, loc_fts.to(f32).contiguous(), nav_types.to(torch.int32).reshape(-1).contiguous(),
-                             keep_idx, anchor)
+                             keep_idx, anchor, fuse)
         ret = {"pano_embeds": pano, "pano_masks": pano_masks}
         if obj_img_fts is not None and obj_img_fts.shape[1] > 0:
             assert self.obj_projector is not None, "object features given but the model was built with enable_og=False"

@@ -512,12 +512,22 @@ class ModifiedLlamaForCausalLM(nn.Module):
     def generate(self, input_ids, attention_mask, cand_vis=None, hist_vis=None, obj_vis=None, max_new_tokens: int = 20,
                  do_sample: bool = False, temperature: float = 1.0, eos_token_id: Optional[int] = None,
                  pad_token_id: Optional[int] = None, bos_token_id: Optional[int] = None, logits_processor=None, trie=None,
-                 stop_on_eos: bool = True, use_cuda_graph: bool = True, stats: Optional[dict] = None, **unused) -> torch.Tensor:
+                 stop_on_eos: bool = True, use_cuda_graph: bool = True, stats: Optional[dict] = None, top_k: int = 50,
+                 top_p: float = 1.0, **unused) -> torch.Tensor:
         """Prefill on the packed kernels (positions = cumsum(mask)-1 like HF generate; visual tokens injected only
         here, as in models/modified_lm.py:195-197), then one token per step over a pre-allocated KV cache.  The
         greedy step has static shapes and is replayed as a CUDA graph (captured once per shape, see ``_decode_state``).
         Returns [B, S0 + n_new] int64 ids (prompt part copied from the input; finished rows continue with pad_token_id
-        like HF greedy search)."""
+        like HF greedy search).
+
+        ``do_sample=True`` follows HF ``sample`` as the reference reaches it (tasks/agents/llava.py:58-62): logits
+        processors, then temperature and top-k (``top_k=50`` is transformers' generation default, which the reference
+        never overrides), bf16 softmax, one multinomial draw per row - all in ``nv_sample_topk``; the uniform numbers
+        come from ``torch.rand`` on the device, so ``torch.manual_seed`` makes a run reproducible."""
+        if top_p is not None and top_p < 1.0:
+            raise NotImplementedError("generate(top_p < 1) is not built: the reference never sets it (HF default 1.0)")
+        if do_sample and not temperature > 0:
+            raise ValueError("generate(do_sample=True) needs temperature > 0")
         self._ensure()
         dev = self._device()
         core, d = self.core, self.dims
@@ -531,6 +541,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
         vis = self.cat_vis(cand_vis, hist_vis, obj_vis, pp)
         B = pp.B
         greedy = (not do_sample) and trie is None and not logits_processor
+        need_host = trie is not None or bool(logits_processor)    # processors walk the generated ids on the host
         graphed = greedy and use_cuda_graph
         Smax = (max(pp.seqlens) + max_new_tokens + 127) // 128 * 128          # bucketed: more reuse of the cached state
         st = self._decode_state(B, Smax, (int(eos), int(pad), bool(stop_on_eos)), graphed)
@@ -557,6 +568,10 @@ class ModifiedLlamaForCausalLM(nn.Module):
             if greedy:
                 ops.argmax_masked(logits, special, finished, eos, pad, stop_on_eos, next_ids)
                 return
+            if not need_host:                                     # plain sampling: straight from the bf16 logits
+                ops.sample_topk(logits, special, finished, eos, pad, stop_on_eos, temperature, top_k,
+                                torch.rand(B, device=dev, dtype=torch.float32), next_ids)
+                return
             lg = logits.float()
             lg[:, self.special_token_ids] = float("-inf")
             if trie is not None:                                  # TrieLogitsProcessor (models/modified_lm.py:10-30)
@@ -572,9 +587,10 @@ class ModifiedLlamaForCausalLM(nn.Module):
             for proc in (logits_processor or []):
                 lg = proc(torch.tensor(all_ids_host, device=dev), lg)
             if do_sample:
-                nxt = torch.multinomial(torch.softmax(lg / max(temperature, 1e-6), dim=-1), 1).squeeze(1)
-            else:
-                nxt = lg.argmax(dim=-1)
+                ops.sample_topk(lg.to(torch.bfloat16), special, finished, eos, pad, stop_on_eos, temperature, top_k,
+                                torch.rand(B, device=dev, dtype=torch.float32), next_ids)
+                return
+            nxt = lg.argmax(dim=-1)
             fin = finished.bool()
             nxt = torch.where(fin, torch.full_like(nxt, pad), nxt)
             if stop_on_eos:
@@ -582,7 +598,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
             next_ids.copy_(nxt.to(torch.int32))
 
         head(hid_last)
-        host_ids = [row.tolist() for row in input_ids.cpu()] if not greedy else None
+        host_ids = [row.tolist() for row in input_ids.cpu()] if need_host else None
         pick(host_ids)
         out_tokens = [next_ids.clone()]
         if ev is not None:
@@ -600,12 +616,12 @@ class ModifiedLlamaForCausalLM(nn.Module):
         # HF stops when every sequence has finished.  Asking the device after EVERY token would serialise host and device
         # (one blocking read per token); finished rows only emit pad tokens, so the greedy loop looks every `check_every`
         # tokens and the surplus pad columns are trimmed below -- same ids as a per-token check.
-        check_every = 8 if greedy else 1
+        check_every = 1 if need_host else 8
         replays = 0
         for it in range(1, max_new_tokens):
             if stop_on_eos and it % check_every == 0 and bool(finished.all()):
                 break
-            if not greedy:
+            if need_host:
                 for bn, t in enumerate(out_tokens[-1].tolist()):
                     host_ids[bn].append(t)
             if graphed:
@@ -632,7 +648,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
             stats.update({"prefill_ms": ev[0].elapsed_time(ev[1]), "decode_ms": ev[1].elapsed_time(ev[2]) if n_dec else None,
                           "decode_steps": n_dec, "graph_replays": replays, "kv_rows": Smax, "prompt_lens": list(pp.seqlens)})
         new = torch.stack(out_tokens, dim=1).to(torch.int64)
-        if stop_on_eos and greedy and new.shape[1] > 1:
+        if stop_on_eos and not need_host and new.shape[1] > 1:
             # trim the columns generated after the step at which the last row emitted EOS (see check_every above)
             is_eos = (new == eos)
             if bool(is_eos.any(dim=1).all()):

@@ -539,6 +539,19 @@ def argmax_masked(logits, special, finished, eos_id, pad_id, stop_on_eos, next_i
     return next_ids
 
 
+def sample_topk(logits, special, finished, eos_id, pad_id, stop_on_eos, temperature, top_k, u, next_ids, probs_out=None):
+    """One sampled token per row (nv_sample_topk): logits [B, V] bf16, u [B] fp32 uniform in [0, 1)."""
+    B, V = logits.shape
+    assert logits.dtype == bf16 and logits.stride(1) == 1 and u.dtype == torch.float32 and u.numel() == B
+    assert next_ids.dtype == torch.int32 and finished.dtype == torch.int32
+    if probs_out is not None:
+        assert probs_out.dtype == torch.float32 and probs_out.shape == (B, V) and probs_out.is_contiguous()
+    check(_lib.load().nv_sample_topk(ptr(logits), i64(logits.stride(0)), i32(V), ptr(special), i32(special.numel()), ptr(finished),
+                                     i32(eos_id), i32(pad_id), i32(1 if stop_on_eos else 0), f32(temperature), i32(top_k), ptr(u),
+                                     ptr(next_ids), ptr(probs_out), i32(B), stream_ptr()), "nv_sample_topk")
+    return next_ids
+
+
 class LayerRunner:
     """Inference forward of decoder layers through nv_llama_layer_infer (csrc/layer.cu): ONE C-ABI call per layer instead of
     ten.  Holds the argument block and a workspace for a given packing; ``run`` fills in what changes per layer."""

@@ -125,8 +125,10 @@ def pano_encoder_layers(x, key_padding_mask, sd, cfg: OracleConfig, prefix="img_
 
 
 def forward_panorama(sd: SD, cfg: OracleConfig, view_img_fts, view_lens, loc_fts=None, nav_types=None,
-                     obj_img_fts=None, obj_lens=None, obj_loc_fts=None) -> Dict[str, torch.Tensor]:
-    """ImageEmbeddings.forward_panorama_per_step (models/image_embedding.py:51-121), eval mode, fuse_obj off."""
+                     obj_img_fts=None, obj_lens=None, obj_loc_fts=None, fuse_obj: bool = False) -> Dict[str, torch.Tensor]:
+    """ImageEmbeddings.forward_panorama_per_step (models/image_embedding.py:51-121), eval mode.  ``fuse_obj`` is the
+    constructor flag of the reference (``--fuse_obj``, tools/parser.py:95): object tokens join the views in the encoder
+    (:78-94); pinned by tests/golden/pano_fuse_obj.pt."""
     P = "img_embeddings."
     x = _ln(_lin(view_img_fts, sd, P + "img_linear"), sd, P + "img_layer_norm", 1e-12)
     if loc_fts is None:
@@ -137,7 +139,25 @@ def forward_panorama(sd: SD, cfg: OracleConfig, view_img_fts, view_lens, loc_fts
     x = x + F.embedding(nav_types.long(), sd[P + "nav_type_embedding.weight"])
     x = _ln(x, sd, P + "layer_norm", 1e-12)
     pano_masks = gen_seq_masks(view_lens)
-    if cfg.num_pano_layers > 0:
+    if cfg.num_pano_layers > 0 and fuse_obj:
+        # :79-94  obj tokens = obj_linear (Linear + LN) + the SHARED loc LN(Linear) + nav-type 2; NOT through layer_norm/dropout;
+        # per row [views[:view_len] ; objs[:obj_len]], zero-padded, encoded with the joint mask; the view rows are taken back
+        o = _ln(_lin(obj_img_fts, sd, P + "obj_linear.0"), sd, P + "obj_linear.1", 1e-12)
+        o = o + _ln(_lin(obj_loc_fts, sd, P + "loc_linear"), sd, P + "loc_layer_norm", 1e-12)
+        o = o + sd[P + "nav_type_embedding.weight"][2]
+        B = x.shape[0]
+        vl, ol = [int(v) for v in view_lens], [int(v) for v in obj_lens]
+        Lf = max(v + w for v, w in zip(vl, ol))
+        fused = x.new_zeros(B, Lf, x.shape[-1])
+        for b in range(B):
+            fused[b, :vl[b]] = x[b, :vl[b]]
+            fused[b, vl[b]:vl[b] + ol[b]] = o[b, :ol[b]]
+        fmask = gen_seq_masks(torch.tensor([v + w for v, w in zip(vl, ol)]))
+        fused = pano_encoder_layers(fused, fmask.logical_not(), sd, cfg)
+        x = x.new_zeros(B, max(vl), x.shape[-1])
+        for b in range(B):
+            x[b, :vl[b]] = fused[b, :vl[b]]
+    elif cfg.num_pano_layers > 0:
         x = pano_encoder_layers(x, pano_masks.logical_not(), sd, cfg)
     x = _lin(x, sd, P + "mapper")
     x = x.masked_fill(pano_masks.logical_not().unsqueeze(-1), 0)
@@ -447,6 +467,26 @@ def greedy_generate(sd: SD, cfg: OracleConfig, input_ids, attention_mask, cand_v
             if not bool(unfinished.any()):
                 break
     return (ids, step_logits) if return_logits else ids
+
+
+def sampling_probs(scores: torch.Tensor, temperature: float = 1.0, top_k: int = 50) -> torch.Tensor:
+    """The distribution HF ``GenerationMixin.sample`` draws the next token from when the reference generates with
+    ``do_sample=True`` (tasks/agents/llava.py:58-62 -> models/nav_model.py:388-396 -> lang_model.generate(**kwargs)):
+    the logits warpers of transformers' generation utilities in their order - TemperatureLogitsWarper
+    (``scores / temperature``, only when != 1) then TopKLogitsWarper (``top_k = 50`` is the generation default the
+    reference never overrides; ``scores < topk(scores, k)[0][..., -1, None]`` -> -inf, so ties at the k-th value stay)
+    - followed by ``softmax(dim=-1)`` IN THE SCORES' DTYPE (bf16 next-token logits in the reference) and
+    ``torch.multinomial(probs, 1)``.  ``scores`` are the next-token logits after the logits processors (special tokens
+    already -inf, models/modified_lm.py:122-124).  Pinned against the installed transformers' warper classes in
+    tests/test_sampling_cpu.py."""
+    s = scores
+    if temperature != 1.0:
+        s = s / temperature
+    if top_k is not None and top_k > 0:
+        k = min(int(top_k), s.shape[-1])
+        kth = torch.topk(s, k)[0][..., -1, None]
+        s = s.masked_fill(s < kth, float("-inf"))
+    return F.softmax(s, dim=-1)
 
 
 # =====================================================================================================

@@ -224,3 +224,34 @@ def test_summarization_generation_branch_matches_reference(precision):
         assert free[:, :n].tolist() == ref[:, :n].tolist()
     else:
         assert free[:, :5].tolist() == ref[:, :5].tolist()                   # later steps may hit a bf16 near-tie
+
+
+def load_fuse_obj():
+    g = torch.load(GOLD / "pano_fuse_obj.pt", weights_only=False)
+    d = g["dims"]
+    cfg = O.OracleConfig(image_feat_size=d["image_feat_size"], obj_feat_size=d["obj_feat_size"], pano_hidden=d["pano_hidden"],
+                         pano_heads=d["pano_heads"], pano_inter=d["pano_inter"], num_pano_layers=d["num_pano_layers"])
+    return g, cfg
+
+
+def test_panorama_fuse_obj_matches_reference():
+    """`--fuse_obj` branch (models/image_embedding.py:78-94): forward outputs and every parameter gradient against the
+    reference's own ImageEmbeddings (tests/golden/make_fuse_obj_golden.py)."""
+    g, cfg = load_fuse_obj()
+    sd = {"img_embeddings." + k: v.clone().requires_grad_(True) for k, v in g["state_dict"].items()}
+    out = O.forward_panorama(sd, cfg, **g["inputs"], fuse_obj=True)
+    assert torch.allclose(out["pano_embeds"], g["pano_embeds"], rtol=2e-5, atol=2e-5)
+    assert torch.allclose(out["obj_embeds"], g["obj_embeds"], rtol=2e-5, atol=2e-5)
+    assert torch.equal(out["pano_masks"], g["pano_masks"]) and torch.equal(out["obj_masks"], g["obj_masks"])
+    loss = (out["pano_embeds"] * g["wp"]).sum() + (out["obj_embeds"] * g["wo"]).sum()
+    assert torch.allclose(loss, g["loss"], rtol=1e-5, atol=1e-4)
+    loss.backward()
+    assert not g["no_grad"]
+    for n, ref in g["grads"].items():
+        got = sd["img_embeddings." + n].grad
+        assert got is not None, n
+        scale = float(ref.abs().max()) + 1e-6
+        assert float((got - ref).abs().max()) <= 2e-5 * scale + 2e-5, n
+    # the branch differs from the plain encoder (object tokens are attended to)
+    plain = O.forward_panorama(sd, cfg, **g["inputs"], fuse_obj=False)["pano_embeds"]
+    assert float((plain - g["pano_embeds"]).abs().max()) > 1e-3

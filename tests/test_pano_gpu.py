@@ -167,3 +167,50 @@ def test_train_mode_dropout_is_applied_and_its_backward_is_consistent(cuda_dev):
             assert abs(num - ana) <= 2e-2 * max(abs(num), abs(ana)) + 2e-2, (name, num, ana)
     finally:
         ops.set_pano_precision(prev)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# `--fuse_obj` branch (models/image_embedding.py:78-94) against the reference's own module (golden fixture)
+# ---------------------------------------------------------------------------------------------------------
+def test_pano_fuse_obj_matches_reference_golden(cuda_dev, pano_precision):
+    """Forward outputs and every parameter gradient of the object-fusing encoder vs tests/golden/pano_fuse_obj.pt (the
+    UNMODIFIED reference ImageEmbeddings(use_obj=True, fuse_obj=True), CPU fp32, eval): ragged view / object counts, one
+    row without objects.  Two backward passes check that gradients accumulate."""
+    from navillm_b200.image_embedding import ImageEmbeddings
+    tol_f, tol_g = (1e-4, 2e-4) if pano_precision == "fp32" else (4e-3, 1e-2)
+    g = torch.load(Path(__file__).resolve().parent / "golden" / "pano_fuse_obj.pt", weights_only=False)
+    d = g["dims"]
+    vis_cfg = types.SimpleNamespace(hidden_size=d["pano_hidden"], num_attention_heads=d["pano_heads"], intermediate_size=d["pano_inter"],
+                                    hidden_dropout_prob=0.1, image_feat_size=d["image_feat_size"], angle_feat_size=4,
+                                    obj_feat_size=d["obj_feat_size"], output_size=d["output_size"], num_pano_layers=d["num_pano_layers"])
+    mod = ImageEmbeddings(vis_cfg, use_obj=True, fuse_obj=True).eval()
+    assert list(mod.state_dict().keys()) == list(g["state_dict"].keys()), "parameter names / order must equal the reference's"
+    mod.load_state_dict(g["state_dict"])
+    mod = mod.to(cuda_dev)
+    inp = {k: v.to(cuda_dev) for k, v in g["inputs"].items()}
+    for rep in (1, 2):
+        out = mod.forward_panorama_per_step(**inp)
+        assert rel_err(out["pano_embeds"].detach().cpu(), g["pano_embeds"]) < tol_f
+        assert rel_err(out["obj_embeds"].detach().cpu(), g["obj_embeds"]) < tol_f
+        assert torch.equal(out["pano_masks"].cpu(), g["pano_masks"]) and torch.equal(out["obj_masks"].cpu(), g["obj_masks"])
+        loss = (out["pano_embeds"] * g["wp"].to(cuda_dev)).sum() + (out["obj_embeds"] * g["wo"].to(cuda_dev)).sum()
+        loss.backward()
+        torch.cuda.synchronize()
+        for name, p in mod.named_parameters():
+            assert p.grad is not None, name
+            assert rel_err(p.grad.cpu() / rep, g["grads"][name]) < tol_g, f"{name} (pass {rep}): {rel_err(p.grad.cpu() / rep, g['grads'][name])}"
+    # without the flag the same weights give the plain encoder (object tokens not attended to)
+    plain = ImageEmbeddings(vis_cfg, use_obj=True, fuse_obj=False).eval()
+    plain.load_state_dict({k: v for k, v in g["state_dict"].items() if not k.startswith("obj_linear.")})
+    plain = plain.to(cuda_dev)
+    p2 = plain.forward_panorama_per_step(**inp)["pano_embeds"]
+    assert rel_err(p2.detach().cpu(), g["pano_embeds"]) > 10 * tol_f
+
+
+def test_pano_fuse_obj_errors(cuda_dev):
+    from navillm_b200.image_embedding import ImageEmbeddings
+    vis_cfg = types.SimpleNamespace(hidden_size=128, num_attention_heads=2, intermediate_size=256, hidden_dropout_prob=0.1,
+                                    image_feat_size=64, angle_feat_size=4, obj_feat_size=48, output_size=256, num_pano_layers=1)
+    mod = ImageEmbeddings(vis_cfg, use_obj=True, fuse_obj=True).eval().to(cuda_dev)
+    with pytest.raises(ValueError):
+        mod.forward_panorama_per_step(torch.randn(1, 4, 64, device=cuda_dev), torch.tensor([4], device=cuda_dev))
