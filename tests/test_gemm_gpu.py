@@ -199,3 +199,25 @@ def test_decode_attn_rope_fused_matches_two_kernels(cuda_dev):
     torch.cuda.synchronize()
     assert torch.equal(got, want)
     assert torch.equal(kc, kc2) and torch.equal(vc, vc2) and torch.equal(q1, qkv)
+
+
+@pytest.mark.parametrize("M", [17, 48, 128, 129, 192, 256, 257, 384, 511])
+@pytest.mark.parametrize("N,K", [(4096, 4096), (12288, 4096), (22016, 4096), (4096, 11008)])
+def test_mid_m_auto_dispatch_is_bit_identical_to_every_tile_variant(cuda_dev, M, N, K):
+    """16 < M < 512 (one forward of a small batch, evaluation rollouts, prefix-reuse suffixes): nv_gemm_bf16's auto rule
+    picks the tile variant per (M, N) from a measured table (tools/midm_bench.py).  Every variant accumulates the k-blocks in
+    the same order, so the choice must not change one output bit - with and without the residual add - and the result
+    matches the fp32 reference."""
+    from navillm_b200 import ops
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    a = (torch.randn((M, K), generator=g) * 0.5).to(cuda_dev, torch.bfloat16)
+    b = (torch.randn((N, K), generator=g) * 0.5).to(cuda_dev, torch.bfloat16)
+    add = torch.randn((M, N), generator=g).to(cuda_dev, torch.bfloat16)
+    for addend in (None, add):
+        auto = ops.gemm(a, b, addend=addend)
+        for bn in (32, 128, 256, 512):
+            if bn == 32 and M > 128:
+                continue
+            assert torch.equal(ops.gemm(a, b, addend=addend, block_n=bn), auto), (bn, addend is not None)
+    ref = a.float() @ b.float().t()
+    assert torch.allclose(ops.gemm(a, b).float(), ref, rtol=1.6e-2, atol=2e-2 * float(ref.abs().max()) / 8)
