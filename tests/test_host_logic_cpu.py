@@ -183,3 +183,48 @@ def test_grad_sync_skips_clean_segments_and_tapers_chunks():
     assert complement(100, 1000, [(400, 700)]) == [(100, 400), (700, 1000)]
     assert complement(100, 1000, [(0, 150), (900, 2000)]) == [(150, 900)]
     assert complement(100, 1000, []) == [(100, 1000)]
+
+
+def test_fuse_obj_row_maps_reproduce_the_reference_layout():
+    """`--fuse_obj` (models/image_embedding.py:81-93): the encoder input row b is [views[b,:vl] ; objs[b,:ol]] zero-padded to
+    max(vl + ol); the view rows are read back afterwards.  The index maps the kernels gather / scatter with must reproduce
+    exactly that layout (built here with torch indexing) and be inverse to each other."""
+    import types
+    import torch
+    from navillm_b200.image_embedding import ImageEmbeddings
+    cfg = types.SimpleNamespace(hidden_size=32, num_attention_heads=2, intermediate_size=64, hidden_dropout_prob=0.1,
+                                image_feat_size=16, angle_feat_size=4, obj_feat_size=12, output_size=48, num_pano_layers=1)
+    mod = ImageEmbeddings(cfg, use_obj=True, fuse_obj=True)
+    assert [k for k in mod.state_dict() if k.startswith("obj_linear")] == ["obj_linear.0.weight", "obj_linear.0.bias",
+                                                                          "obj_linear.1.weight", "obj_linear.1.bias"]
+    B, N, O = 3, 5, 4
+    vl, ol = torch.tensor([5, 2, 4]), torch.tensor([3, 0, 4])
+    obj = torch.randn(B, O, 12)
+    m = mod._fuse_maps(vl, obj, ol, torch.randn(B, O, 7), B, N, "cpu")
+    Nf = int((vl + ol).max())
+    assert m["Nf"] == Nf and m["lens_f"].tolist() == (vl + ol).tolist() and m["twos"].tolist() == [2] * (B * O)
+    views = torch.arange(B * N, dtype=torch.float32).view(B, N) + 1          # view row ids 1..
+    objs = -(torch.arange(B * O, dtype=torch.float32).view(B, O) + 1)        # object row ids -1..
+    want = torch.zeros(B, Nf)
+    for b in range(B):
+        want[b, :vl[b]] = views[b, :vl[b]]
+        want[b, vl[b]:vl[b] + ol[b]] = objs[b, :ol[b]]
+
+    def gather(src, idx):
+        out = torch.zeros(idx.numel())
+        ok = idx >= 0
+        out[ok] = src.reshape(-1)[idx[ok].long()]
+        return out
+    fused = gather(views, m["view_src"]) + gather(objs, m["obj_src"])
+    assert torch.equal(fused.view(B, Nf), want)
+    back = gather(fused, m["view_back"]).view(B, N)
+    for b in range(B):
+        assert torch.equal(back[b, :vl[b]], views[b, :vl[b]]) and bool((back[b, vl[b]:] == 0).all())
+    oback = gather(fused, m["obj_back"]).view(B, O)
+    for b in range(B):
+        assert torch.equal(oback[b, :ol[b]], objs[b, :ol[b]]) and bool((oback[b, ol[b]:] == 0).all())
+    # a model built without objects cannot fuse them
+    import pytest
+    plain = ImageEmbeddings(cfg, use_obj=False, fuse_obj=True)
+    with pytest.raises(RuntimeError):
+        plain._fuse_maps(vl, obj, ol, torch.randn(B, O, 7), B, N, "cpu")
