@@ -251,6 +251,17 @@ class DistributedDataParallel(torch.nn.parallel.DistributedDataParallel):
                 import warnings
                 warnings.warn(f"navillm_b200: NVLS gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL all-reduce")
                 module.grad_sync.reducer = None
+            # every rank must take the same transport: one rank on NCCL and another in the switch would never meet
+            dist = _dist()
+            if dist is not None:
+                ok = torch.tensor([1 if module.grad_sync.reducer is not None else 0], dtype=torch.int32,
+                                  device=next(module.parameters()).device)
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+                if int(ok.item()) == 0 and module.grad_sync.reducer is not None:
+                    import warnings
+                    warnings.warn("navillm_b200: another rank could not set up the NVLS exchange; all ranks use NCCL")
+                    module.grad_sync.reducer = None       # the symmetric buffers stay in use as ordinary gradient buffers
+                self.nvls = module.grad_sync.reducer is not None
 
     def broadcast_parameters(self, src: int = 0) -> None:
         """DDP's construction-time parameter broadcast: one broadcast per flat weight buffer once they exist
