@@ -24,8 +24,8 @@ import torch.nn as nn
 
 from . import ops
 
-# decode GEMMs: 0 = swap-AB skinny kernel for batches <= 16 (csrc/gemm_skinny.cu, default); 128 / 32 = column-tile
-# width of the general kernel (always used for 16 < batch <= 128)
+# decode GEMMs: 0 (default) = swap-AB skinny kernel for batches <= 16 (csrc/gemm_skinny.cu), nv_gemm_bf16's measured tile
+# table above that; 128 / 32 = force that column-tile width of the general kernel (A/B measurements)
 DECODE_BLOCK_N = int(os.environ.get("NAVILLM_DECODE_BLOCK_N", "0"))
 # weight-gradient GEMMs on a side stream (see LlamaCore.backward)
 WGRAD_STREAM = os.environ.get("NAVILLM_WGRAD_STREAM", "0") != "0"
@@ -509,16 +509,16 @@ class LlamaCore:
         [B, D] before the final RMSNorm."""
         d = self.d
         H, D = d.n_heads, d.hidden
-        # M <= 128 is HBM-bound weight streaming.  Batches <= 16 use the swap-AB cluster-split-K kernel; the general
-        # kernel with 128-column tiles (activations on the UMMA M side) leaves most SMs idle on the 4096-wide
-        # projections (32 tiles) and re-stages a mostly-zero 128-row activation tile per k-block.
+        # The step is HBM-bound weight streaming.  Batches <= 16 use the swap-AB cluster-split-K kernel with the SwiGLU fused
+        # (gemm_skinny.cu); larger batches go through nv_gemm_bf16's auto dispatch, which picks the tile variant per (M, N)
+        # from a measured table (32-column tiles for the 4096-wide projections, 256 for gate|up: tools/midm_bench.py).
         bn = DECODE_BLOCK_N
         skinny = bn == 0 and x.shape[0] <= 16
         fuse_mlp = skinny and d.inter % 64 == 0
         if skinny:
             lin = lambda a, w, addend=None: ops.gemm_skinny(a, w, addend=addend)
         else:
-            lin = lambda a, w, addend=None: ops.gemm(a, w, addend=addend, block_n=bn or 128)
+            lin = lambda a, w, addend=None: ops.gemm(a, w, addend=addend, block_n=bn)
         for l, lyr in enumerate(self.model.layers):
             xn, _ = ops.rmsnorm_fwd(x, lyr.input_layernorm.weight.data, d.rms_eps)
             qkv = lin(xn, self.wqkv[l])

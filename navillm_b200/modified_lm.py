@@ -559,7 +559,7 @@ class ModifiedLlamaForCausalLM(nn.Module):
             if B <= 16 and llama_mod.DECODE_BLOCK_N == 0:
                 ops.gemm_skinny(hn, self.lm_head.weight.data, out=logits)
             else:
-                ops.gemm(hn, self.lm_head.weight.data, out=logits, block_n=128)
+                ops.gemm(hn, self.lm_head.weight.data, out=logits, block_n=llama_mod.DECODE_BLOCK_N)
 
         trie_state = [None]
 

@@ -49,6 +49,45 @@ def test_greedy_generate_matches_oracle(cuda_dev):
         assert sum(matched) >= ids.shape[0] * n_new // 2, f"too few bit-exact tokens before near-ties: {matched}"
 
 
+def test_greedy_generate_batch_over_16_rows(cuda_dev):
+    """Batches above 16 rows leave the M <= 16 decode kernel: their per-token GEMMs go through nv_gemm_bf16's auto dispatch
+    (tile variant per (M, N) from the measured table) and the unfused SwiGLU.  20 rows = the golden prompts repeated; every
+    row must reproduce the oracle's ids of its source row (the oracle is row-independent), with and without the CUDA graph."""
+    from oracle import navillm_oracle as O
+    from tests.test_navmodel_gpu import build_model
+    from tests.test_oracle_golden import load
+    from tests.test_fullwidth_parity_gpu import compare_greedy_rows
+    g, cfg, tok = load("amp_bf16")
+    model, _ = build_model(g, cuda_dev)
+    sd = g["state_dict"]
+    qa = g["qa_in"]
+    n_new, rep = 8, 10
+    feats = qa["features"]
+    lens = torch.tensor([f.shape[0] for f in feats])
+    view = torch.stack([torch.cat([f, f.new_zeros(int(lens.max()) - f.shape[0], f.shape[1])], 0) for f in feats], 0)
+    pano = O.forward_panorama(sd, cfg, view, lens)
+    pe = pano["pano_embeds"] + O._pos_embed(torch.zeros(pano["pano_embeds"].shape[:2] + (14,)), sd, "vp_pos_embeddings")
+    pe = pe + sd["token_type_embeddings.weight"][0]
+    cand = pe[pano["pano_masks"]]
+    text = tok(qa["prompts"])
+    ref_ids, ref_logits = O.greedy_generate(sd, cfg, text["input_ids"], text["attention_mask"], cand_vis=cand,
+                                            max_new_tokens=n_new, stop_on_eos=False, return_logits=True)
+    S0 = text["input_ids"].shape[1]
+    B0 = text["input_ids"].shape[0]
+    ids_in = text["input_ids"].repeat(rep, 1)
+    mask_in = text["attention_mask"].repeat(rep, 1)
+    cand_in = cand.repeat(rep, 1)                                   # <cand> rows are consumed batch-major: same order per copy
+    big_ref = ref_ids.repeat(rep, 1)
+    big_logits = [lg.repeat(rep, 1) for lg in ref_logits]
+    assert ids_in.shape[0] == B0 * rep > 16
+    for graph in (False, True):
+        ids = model.lang_model.generate(input_ids=ids_in, attention_mask=mask_in, cand_vis=cand_in.to(cuda_dev), max_new_tokens=n_new,
+                                        stop_on_eos=False, use_cuda_graph=graph).cpu()
+        assert ids.shape == big_ref.shape
+        matched, cut = compare_greedy_rows(ids, big_ref, big_logits, S0, n_new, tag=f"B={B0 * rep} graph={graph}")
+        assert sum(matched) >= ids.shape[0] * n_new // 2, f"too few bit-exact tokens before near-ties: {matched}"
+
+
 def test_3dqa_generate_mode_runs_and_decodes(cuda_dev):
     from tests.test_navmodel_gpu import build_model, to_dev
     g = torch.load(GOLD / "nav_amp_bf16.pt", weights_only=False)
