@@ -111,6 +111,9 @@ int nv_rmsnorm_bwd(const void* x, int64_t ldx, const void* w, const float* rstd,
 int nv_rope_inplace(void* qkv, int64_t ld, const int* pos, const void* cos_t, const void* sin_t, int T, int n_heads,
                     int head_dim, int backward, void* stream);
 int nv_swiglu_fwd(const void* gu, int64_t ldgu, void* h, int64_t ldh, int T, int F, void* stream);
+/* x[rows, cols] (bf16, leading dimension ld, even) *= scale[0] (device fp32 scalar), rounded to bf16: the upstream gradient of
+ * the scalar LM loss folded into the stored dlogits (autograd of CrossEntropyLoss, models/modified_lm.py:126-137). */
+int nv_scale_bf16(void* x, int64_t ld, int rows, int cols, const float* scale, void* stream);
 int nv_swiglu_bwd(const void* gu, int64_t ldgu, const void* dh, int64_t lddh, void* dgu, int64_t lddgu, int T, int F,
                   void* stream);
 int nv_embed_fwd(const int* ids, const void* E, int V, const int* vis_src, const float* vis, void* out, int T, int D,

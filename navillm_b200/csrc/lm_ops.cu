@@ -262,6 +262,27 @@ __global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, int64_t 
   }
 }
 
+// x[r, c] = bf16(x[r, c] * s[0]) in place, s a device scalar: folds the upstream gradient of a scalar loss into the stored
+// dlogits without a host read of it (autograd hands CrossEntropyLoss's backward the same factor, models/modified_lm.py:126-137).
+__global__ void scale_bf16_kernel(__nv_bfloat16* __restrict__ x, int64_t ld, int rows, int cols, const float* __restrict__ s) {
+  const float f = s[0];
+  const int pairs = cols >> 1;
+  const int64_t total = (int64_t)rows * pairs;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = idx % pairs;
+    const int64_t r = idx / pairs;
+    uint32_t* p = reinterpret_cast<uint32_t*>(x + r * ld) + c;            // ld even: 4-byte aligned pairs
+    const uint32_t v = *p;
+    *p = pack_bf16x2(bf16_lo(v) * f, bf16_hi(v) * f);
+  }
+  if (cols & 1) {
+    for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+      __nv_bfloat16* q = x + r * ld + (cols - 1);
+      *q = __float2bfloat16_rn(__bfloat162float(*q) * f);
+    }
+  }
+}
+
 __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, int64_t ldgu,
                                   const __nv_bfloat16* __restrict__ dh, int64_t lddh, __nv_bfloat16* __restrict__ dgu,
                                   int64_t lddgu, int T, int F) {
@@ -573,6 +594,14 @@ int nv_swiglu_fwd(const void* gu, int64_t ldgu, void* h, int64_t ldh, int T, int
   NV_REQUIRE((F & 7) == 0 && (ldgu & 7) == 0 && (ldh & 7) == 0, "nv_swiglu_fwd: alignment");
   if (T == 0) return NV_OK;
   swiglu_fwd_kernel<<<grid_for((int64_t)T * (F >> 3), 256), 256, 0, S_(stream)>>>(CBF(gu), ldgu, BF(h), ldh, T, F);
+  NV_LAUNCH_CHECK();
+  return NV_OK;
+}
+
+int nv_scale_bf16(void* x, int64_t ld, int rows, int cols, const float* scale, void* stream) {
+  NV_REQUIRE(x && scale && (ld & 1) == 0 && rows >= 0 && cols >= 0, "nv_scale_bf16: null pointer or odd leading dimension");
+  if (rows == 0 || cols == 0) return NV_OK;
+  scale_bf16_kernel<<<grid_for((int64_t)rows * ((cols + 1) >> 1), 256), 256, 0, S_(stream)>>>(BF(x), ld, rows, cols, scale);
   NV_LAUNCH_CHECK();
   return NV_OK;
 }

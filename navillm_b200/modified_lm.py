@@ -82,7 +82,14 @@ class PackedPrompt:
             loss_rows = np.zeros(0, dtype=np.int64)
             loss_tgt = np.zeros(0, dtype=np.int64)
         self.n_cls, self.n_loss = int(cls_rows.size), int(loss_rows.size)
-        parts = [tok, pos, cu, vis_src, cls_rows, last_rows, loss_rows, loss_tgt]
+        # token order of the deterministic embedding-gradient kernel (one owner per distinct id): sorted on the host, where
+        # the ids already are, instead of a device radix sort per backward
+        if torch.is_grad_enabled():
+            tok_order = np.argsort(tok, kind="stable")
+            tok_sorted = tok[tok_order]
+        else:
+            tok_order = tok_sorted = np.zeros(0, dtype=np.int64)
+        parts = [tok, pos, cu, vis_src, cls_rows, last_rows, loss_rows, loss_tgt, tok_order, tok_sorted]
         host = np.concatenate([p.astype(np.int32) for p in parts])
         buf = torch.from_numpy(host).pin_memory() if torch.cuda.is_available() else torch.from_numpy(host)
         dev = buf.to(device, non_blocking=True)
@@ -92,7 +99,8 @@ class PackedPrompt:
         for p in parts:
             views.append(dev[o:o + p.size])
             o += p.size
-        (self.ids, self.pos, self.cu, self.vis_src, self.cls_rows, self.last_rows, self.loss_rows, self.loss_tgt) = views
+        (self.ids, self.pos, self.cu, self.vis_src, self.cls_rows, self.last_rows, self.loss_rows, self.loss_tgt,
+         self.tok_order, self.tok_sorted) = views
         self.flat_rows = flat_rows                                        # host copy (unpacking to [B,S])
 
 
@@ -232,13 +240,14 @@ class _LMFn(torch.autograd.Function):
             g, rstd, hn, dlogits = ctx.saved
             lm._lm_head_grad_clean = False
             # dlogits was produced with scale 1/N; fold the incoming scalar gradient in on the device (no sync)
-            dlogits.copy_(dlogits.float() * dout.float())        # in place: keeps the 16-byte-aligned row stride
+            ops.scale_(dlogits, dout.detach().to(torch.float32).reshape(1))   # in place: keeps the 16-byte-aligned row stride
             dy = ops.gemm(dlogits, lm.lm_head.weight.data, b_mn=True)                    # [Nl, D]
             ops.gemm(dlogits, hn, a_mn=True, b_mn=True, out=lm.lm_head.weight.grad, addend=lm.lm_head.weight.grad)
         dg = ops.rmsnorm_bwd(g, normw.data, rstd, dy, dw=normw.grad)                     # [R, D]: gradient at the requested rows
         lm.grad_sync.short_backward = pp.T < lm.SHORT_BACKWARD_TOKENS
         dx = core.backward(dg, ctx.tape, layer_done=lm._grad_sync_hook())
-        ops.embed_bwd_weight_(dx, pp.ids, lm.model.embed_tokens.weight.grad)
+        ops.embed_bwd_weight_(dx, pp.ids, lm.model.embed_tokens.weight.grad,
+                              order=pp.tok_order if pp.tok_order.numel() == pp.T else None, sorted_ids=pp.tok_sorted)
         dvis = ops.embed_bwd_vis(dx, pp.vis_src, ctx.n_vis) if ctx.has_vis else None
         ctx.saved = ctx.tape = None
         return None, None, dvis, None, None, None, None

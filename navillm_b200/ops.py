@@ -190,6 +190,14 @@ def swiglu_bwd(gu, dh, *, out=None):
     return out
 
 
+def scale_(x: torch.Tensor, scale: torch.Tensor) -> torch.Tensor:
+    """x[rows, cols] (bf16, unit inner stride, even row stride) *= scale (a one-element fp32 CUDA tensor), in place."""
+    _rowmajor(x, "x")
+    assert x.dtype == bf16 and scale.dtype == torch.float32 and scale.numel() == 1 and scale.is_cuda
+    check(_lib.load().nv_scale_bf16(ptr(x), i64(x.stride(0)), i32(x.shape[0]), i32(x.shape[1]), ptr(scale), stream_ptr()), "nv_scale_bf16")
+    return x
+
+
 def embed_fwd(ids, E, vis_src=None, vis=None, *, out=None):
     T = ids.numel()
     V, D = E.shape
@@ -211,13 +219,17 @@ def embed_bwd_vis(dx, vis_src, n_vis):
     return dvis
 
 
-def embed_bwd_weight_(dx, ids, dE):
-    """dE[ids[t]] += dx[t] (deterministic: tokens are sorted by id, one owner per distinct id)."""
+def embed_bwd_weight_(dx, ids, dE, *, order=None, sorted_ids=None):
+    """dE[ids[t]] += dx[t] (deterministic: tokens are sorted by id, one owner per distinct id).  ``order`` / ``sorted_ids``:
+    the stable argsort of ``ids`` and the sorted ids as int32 device tensors when the caller has them (PackedPrompt sorts
+    on the host, where the ids come from); otherwise they are computed here."""
     T, D = dx.shape
-    sorted_ids, order = torch.sort(ids.to(torch.int64), stable=True)
+    if order is None or sorted_ids is None:
+        sorted_ids, order = torch.sort(ids.to(torch.int64), stable=True)
     # keep the int32 copies referenced until after the launch: a temporary freed inside the argument
     # list would hand its block back to the caching allocator before the kernel reads it
     order32, sorted32 = order.to(torch.int32), sorted_ids.to(torch.int32)
+    assert order32.numel() == T and sorted32.numel() == T
     check(_lib.load().nv_embed_bwd_weight(ptr(dx), ptr(order32), ptr(sorted32), ptr(dE), i32(T), i32(D), stream_ptr()),
           "nv_embed_bwd_weight")
     return dE

@@ -54,6 +54,11 @@ def test_packed_prompt_indices():
     assert (ids[rows + 1] == tgt).all() and pp.n_loss == int((labels[:, 1:] != -100).sum())
     gen = PackedPrompt(text["input_ids"], text["attention_mask"], lm, torch.device("cpu"), generate_positions=True)
     assert gen.pos[:3].tolist() == [0, 1, 2]                          # generate: cumsum(mask) - 1
+    # token order for the deterministic embedding gradient: the stable argsort torch.sort would give, made on the host
+    ref_sorted, ref_order = torch.sort(pp.ids.to(torch.int64), stable=True)
+    assert pp.tok_order.tolist() == ref_order.tolist() and pp.tok_sorted.tolist() == ref_sorted.tolist()
+    with torch.no_grad():                                             # inference: no backward, no sort, nothing uploaded
+        assert PackedPrompt(text["input_ids"], text["attention_mask"], lm, torch.device("cpu")).tok_order.numel() == 0
 
 
 def test_oracle_rope_tables_match_product_tables():

@@ -156,3 +156,19 @@ def test_ce(cuda_dev):
     loss.backward()
     close(row_loss.sum() / n_act, loss.detach(), 1e-4, 1e-4)
     close(dl, la.grad, 1.6e-2, 1e-6)
+
+
+@pytest.mark.parametrize("cols", [32006, 33, 8])
+def test_scale_in_place_by_a_device_scalar(cuda_dev, cols):
+    """nv_scale_bf16 (the upstream gradient of the scalar LM loss folded into the stored dlogits): equals the fp32 product
+    rounded once to bf16, leaves the padding columns of the strided buffer alone."""
+    from navillm_b200 import ops
+    ld = (cols + 7) // 8 * 8 + 8
+    g = torch.Generator(device="cpu").manual_seed(cols)
+    buf = torch.randn(5, ld, generator=g).to(cuda_dev, torch.bfloat16)
+    keep = buf.clone()
+    x = buf[:, :cols]
+    s = torch.tensor([0.37], device=cuda_dev, dtype=torch.float32)
+    ops.scale_(x, s)
+    assert torch.equal(x, (keep[:, :cols].float() * 0.37).to(torch.bfloat16))
+    assert torch.equal(buf[:, cols:], keep[:, cols:])
